@@ -1,0 +1,189 @@
+/*
+ * nsagp.h -- C ABI of libnsagp.so: the B200 (sm_100a) implementation of the
+ * EP-in-Kalman inference hot path of AaltoML/nonstationary-audio-gp.
+ *
+ * This is the drop-in boundary.  The reference has no FFI (it is 100 % MATLAB);
+ * these entry points are what a MEX gateway for its entry functions binds
+ * (INTEGRATION.md shows the gateway and the .m wrappers).  Each function cites
+ * the reference interface it replaces.  Conventions:
+ *   - all floating point data is IEEE FP64, matrices are column-major
+ *     (MATLAB layout), so M-by-T site arrays are contiguous per time step;
+ *   - every buffer is caller-owned HOST memory unless the name says "dev";
+ *     the library copies to/from the GPU itself and allocates nothing the
+ *     caller can see;
+ *   - NaN in y marks a missing / test-only sample (gf_ep_modulator_nmf.m:59);
+ *   - functions return NSAGP_OK or a negative nsagp_status; nsagp_last_error()
+ *     gives the message.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point returns NSAGP_ERR_CUDA.
+ */
+#ifndef NSAGP_H
+#define NSAGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum nsagp_status {
+  NSAGP_OK = 0,
+  NSAGP_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  NSAGP_ERR_CUDA = -2,        /* CUDA runtime failure (message has the detail) */
+  NSAGP_ERR_NOT_PD = -3,      /* smoother Cholesky failed; the reference would add
+                                 rand() jitter here (gf_ep_modulator_nmf.m:216-223) */
+  NSAGP_ERR_NONPOS_VAR = -4,  /* predictive variance <= 0; the reference drops into
+                                 `keyboard` (gf_ep_modulator_nmf.m:408-410) */
+  NSAGP_ERR_NAN = -5          /* NaN energy (gf_giekf_modulator_nmf_constraints.m:423-426) */
+} nsagp_status;
+
+/* Discrete-time model in block form.  Replaces the dense (A,Q,H,Pinf) the
+ * reference builds with ss(...) + lti_disc(...) (gf_ep_modulator_nmf.m:78,108;
+ * ihgp_ep_modulator_nmf.m:79-97): those matrices are block diagonal with one
+ * block and one observation row per latent (ss_modulators_nmf.m:128-132).
+ * D subband blocks of size bz come first, then N modulator blocks of size bg.
+ * A, Q, Pinf: packed b-by-b blocks, column-major, D*bz*bz + N*bg*bg doubles.
+ * h: packed observation rows, D*bz + N*bg doubles. */
+typedef struct nsagp_model {
+  int32_t D, N;
+  int32_t bz, bg;             /* 1..8 each */
+  const double* A;
+  const double* Q;
+  const double* Pinf;
+  const double* h;
+} nsagp_model;
+
+/* Likelihood / moment-matching closure.  Replaces the `mom` function handle
+ * (demo_toy_modulators_nmf.m:81, experiments/train_model.m:190), resolved to
+ *   kind 0: likModulatorNMFPower.m:28-87     a(g) = W*link(g),       pEP_const = 1
+ *   kind 1: experiments/likModulatorPreCalcwn.m:28-86
+ *                                            a(g) = sqrt(W*link(g)), pEP_const = (2 pi sn2)^((1-alpha)/2) alpha^(-1/2)
+ * with link(g) = log(1+exp(g - link_shift)).  (wn, xn) are the unit sigma points
+ * of utp_ws(p,N) or mvhermgauss: wn[S], xn N-by-S column-major. */
+typedef struct nsagp_lik {
+  int32_t kind;
+  double sn2;                 /* exp(lik_param) */
+  double link_shift;
+  const double* W;            /* D-by-N, column-major */
+  int32_t S;
+  const double* wn;
+  const double* xn;
+} nsagp_lik;
+
+/* EP schedule: ep_fraction (Power-EP alpha), ep_damping[ep_itts], ep_itts
+ * (arguments 12-14 of gf_ep_modulator_nmf.m:1). */
+typedef struct nsagp_ep {
+  double ep_fraction;
+  const double* ep_damping;
+  int32_t ep_itts;
+} nsagp_ep;
+
+/* Steady-state tables of the infinite-horizon path
+ * (ihgp_ep_modulator_nmf.m:131-133 PPlist, :183-189 PGlist), built on the host.
+ * r[nr] ascending grid of equivalent noise variances.  PP: per block nr rows of
+ * b*b doubles (column-major b-by-b), blocks concatenated.  PG: per block nr rows
+ * of 2*b*b doubles [smoothed covariance, smoother gain]; may be NULL in nlZ mode. */
+typedef struct nsagp_tables {
+  int32_t nr;
+  const double* r;
+  const double* PP;
+  const double* PG;
+} nsagp_tables;
+
+typedef enum nsagp_mode {
+  NSAGP_MODE_PREDICT = 0,     /* xt non-empty: posterior marginals            */
+  NSAGP_MODE_NLZ = 1,         /* xt empty: negative log marginal likelihood   */
+  NSAGP_MODE_NLZ_RUNNING = 2  /* ihgp ..._constraints nlZ mode: site vectors carried
+                                 from step to step (ihgp_ep_modulator_nmf_constraints.m:568-615) */
+} nsagp_mode;
+
+/* Output buffers (any pointer may be NULL = not wanted).  Shapes as in the
+ * reference's outputs: M = D+N sites, n = state dimension, T steps.
+ *   Eft, Varft, lb, ub : M-by-T     (gf_ep_modulator_nmf.m:321-348)
+ *   ttau, tnu, R       : M-by-T     (out.ttau, out.tnu, out.R)
+ *   lZ                 : T          (out.lZ; ihgp: per-step terms of the last pass)
+ *   MF, MS             : n-by-T     (out.MF filtered, out.MS smoothed means)
+ *   PF, PS             : packed blocks, (D*bz*bz+N*bg*bg)-by-T (block form of out.PF/out.PS)
+ *   nlZ                : ep_itts    (nlZ(itt) trace printed by the reference)
+ *   maxDiffM, maxDiffP : ep_itts    (convergence diagnostics, :271-272)
+ *   edata              : 1          (nlZ mode: -sum(lZ), :525)
+ *   n_negcav           : 1          (count of cavity variances <= 0; the reference
+ *                                    silently goes complex there) */
+typedef struct nsagp_outputs {
+  double* Eft; double* Varft; double* lb; double* ub;
+  double* ttau; double* tnu; double* R; double* lZ;
+  double* MF; double* MS; double* PF; double* PS;
+  double* nlZ; double* maxDiffM; double* maxDiffP;
+  double* edata;
+  int64_t* n_negcav;
+} nsagp_outputs;
+
+const char* nsagp_version(void);
+const char* nsagp_last_error(void);
+
+/* Select the CUDA device used by the calling thread's subsequent calls and the
+ * stream the kernels are launched on (0 = the library's own stream). */
+int nsagp_set_device(int device);
+int nsagp_set_stream(void* cuda_stream);
+int nsagp_device_count(void);
+
+/* Number of kernel launches issued by this library since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t nsagp_launch_count(int reset);
+
+/* likModulatorNMFPower / likModulatorPreCalcwn for a batch of independent
+ * calls: for k < T, [lZ(k), dlZ(:,k), d2lZ(:,k)] = mom(y(k), mu(:,k), s2(:,k), ep_fraction)
+ * (likModulatorNMFPower.m:28-87).  mu, s2, dlZ, d2lZ are M-by-T. */
+int nsagp_mom_batch(const nsagp_lik* lik, int32_t D, int32_t N, double ep_fraction,
+                    int64_t T, const double* y, const double* mu, const double* s2,
+                    double* lZ, double* dlZ, double* d2lZ);
+/* Same contract, computed by the warp-cooperative form of the moment kernel (the
+ * one the sequential ADF pass uses); exposed so parity tests reach it directly. */
+int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_fraction,
+                         int64_t T, const double* y, const double* mu, const double* s2,
+                         double* lZ, double* dlZ, double* d2lZ);
+
+/* ihgp_ep_modulator_nmf / ihgp_ep_modulator_nmf_constraints
+ * (ihgp_ep_modulator_nmf.m:195-526 predict, :533-624 nlZ).  y[T] is `yall` after
+ * the merge/sort of train and test inputs (:58-67). */
+int nsagp_ep_ihgp(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep,
+                  const nsagp_tables* tables, const double* y, int64_t T,
+                  int32_t mode, nsagp_outputs* out);
+
+/* gf_ep_modulator_nmf / gf_ep_modulator_nmf_constraints
+ * (gf_ep_modulator_nmf.m:92-352 predict, :357-533 nlZ). */
+int nsagp_ep_full(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep,
+                  const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
+
+/* Batched forms: B independent problems of equal shapes (clips x hyper-parameter
+ * grid x finite-difference perturbations; what fminunc does around the nlZ mode,
+ * demo_toy_modulators_nmf.m:100-104).  models/liks/tables/outs are arrays of B
+ * structs, y is T-by-B column-major (one clip per column). */
+int nsagp_ep_ihgp_batch(int32_t B, const nsagp_model* models, const nsagp_lik* liks,
+                        const nsagp_ep* ep, const nsagp_tables* tables, const double* y,
+                        int64_t T, int32_t mode, nsagp_outputs* outs);
+int nsagp_ep_full_batch(int32_t B, const nsagp_model* models, const nsagp_lik* liks,
+                        const nsagp_ep* ep, const double* y, int64_t T, int32_t mode,
+                        nsagp_outputs* outs);
+
+/* Device-resident plan API (what the host-buffer calls above are built from; the
+ * benchmark uses it to time the sweep with inputs already in HBM).
+ *   create : uploads model, likelihood, tables and y for B problems
+ *   run    : executes the whole EP schedule on the device (no host copies)
+ *   fetch  : copies the requested outputs of problem b back to the host
+ * kind: 0 = ihgp, 1 = full-state EP. */
+typedef struct nsagp_plan nsagp_plan;
+int nsagp_plan_create(nsagp_plan** plan, int32_t kind, int32_t B, const nsagp_model* models,
+                      const nsagp_lik* liks, const nsagp_ep* ep, const nsagp_tables* tables,
+                      const double* y, int64_t T, int32_t mode);
+int nsagp_plan_run(nsagp_plan* plan);
+int nsagp_plan_fetch(nsagp_plan* plan, int32_t b, nsagp_outputs* out);
+int nsagp_plan_destroy(nsagp_plan* plan);
+/* Device time (ms, CUDA events on the launch stream) of the phases of the last
+ * nsagp_plan_run: [0] total, [1] ADF filter pass, [2] fixed-site filter passes,
+ * [3] smoother passes, [4] site-update passes.  Returns the number written. */
+int nsagp_plan_timings(nsagp_plan* plan, double* ms, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSAGP_H */

@@ -1,0 +1,801 @@
+// C ABI of libnsagp.so (include/nsagp.h): plan construction, host orchestration
+// of the EP schedule, result fetch.  No CPU compute path exists here: every
+// entry point either runs the CUDA kernels or returns an error.
+#include "../../include/nsagp.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gfep.cuh"
+#include "ihgp.cuh"
+#include "mombatch.cuh"
+
+using namespace nsagp;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local cudaStream_t g_stream = nullptr;
+thread_local bool g_own_stream = false;
+long long g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(NSAGP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                        \
+  do {                                                                                        \
+    ++g_launches;                                                                             \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(NSAGP_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));   \
+  } while (0)
+
+int ensure_stream() {
+  if (g_stream == nullptr) {
+    CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_own_stream = true;
+  }
+  return NSAGP_OK;
+}
+
+int round_bm(int b) {
+  const int opts[] = {2, 3, 4, 6, 8};
+  for (int o : opts) if (b <= o) return o;
+  return -1;
+}
+
+// Smallest double x in (lo, hi] with nearest(x) > i, by bisection over bit patterns.
+double bisect_threshold(const std::vector<double>& r, int i) {
+  auto above = [&](double x) { return nearest_bruteforce(r.data(), (int)r.size(), x) > i; };
+  uint64_t lo, hi;
+  double a = r[i], b = r[i + 1];
+  std::memcpy(&lo, &a, 8);
+  std::memcpy(&hi, &b, 8);      // positive doubles: bit patterns are ordered
+  // invariant: !above(lo), above(hi)
+  while (hi - lo > 1) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    double x;
+    std::memcpy(&x, &mid, 8);
+    if (above(x)) hi = mid; else lo = mid;
+  }
+  double x;
+  std::memcpy(&x, &hi, 8);
+  return x;
+}
+
+struct DeviceArena {
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  template <class T>
+  int alloc(T** p, size_t count) {
+    void* q = nullptr;
+    const size_t nb = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, nb);
+    if (e != cudaSuccess) return fail(NSAGP_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    ptrs.push_back(q);
+    bytes += nb;
+    *p = static_cast<T*>(q);
+    return NSAGP_OK;
+  }
+  template <class T>
+  int upload(T** p, const std::vector<T>& h) {
+    int rc = alloc(p, h.size());
+    if (rc) return rc;
+    if (!h.empty()) CU(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return NSAGP_OK;
+  }
+  void release() {
+    for (void* q : ptrs) cudaFree(q);
+    ptrs.clear();
+  }
+};
+
+}  // namespace
+
+struct nsagp_plan {
+  int kind = 0, B = 0, mode = 0;
+  long long T = 0;
+  int D = 0, N = 0, M = 0, bz = 0, bg = 0, BM = 0, n = 0, DP = 0, S = 0, nr = 0, PB = 0;
+  double alpha = 1.0;
+  std::vector<double> damping;
+  int ep_itts = 1;
+  DeviceArena arena;
+  std::vector<DevProblem> h_probs;
+  std::vector<DevState> h_states;
+  DevProblem* d_probs = nullptr;
+  DevState* d_states = nullptr;
+  double* d_chunk = nullptr;
+  double* d_start = nullptr;
+  double* d_nlZ = nullptr;      // [B][ep_itts + 1]  (last slot: edata)
+  double* d_diag = nullptr;     // [B][ep_itts][2]
+  double* d_MF = nullptr;       // [B][T][n] filtered means of the last pass (predict mode)
+  double* d_PF = nullptr;       // [B][T][PB] filtered covariances of the last pass (full-state, predict)
+  double* d_y = nullptr;
+  std::vector<double> h_vminf;  // [B][M] h Pinf h'
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> phase_ev;
+  double timings[5] = {0, 0, 0, 0, 0};
+  bool ran = false;
+};
+
+namespace {
+
+int validate_shapes(int B, const nsagp_model* models, const nsagp_lik* liks, const nsagp_ep* ep, long long T) {
+  if (B < 1 || !models || !liks || !ep) return fail(NSAGP_ERR_INVALID, "null argument or B < 1");
+  if (T < 1) return fail(NSAGP_ERR_INVALID, "T must be >= 1");
+  if (ep->ep_itts < 1 || !ep->ep_damping) return fail(NSAGP_ERR_INVALID, "ep_itts >= 1 and ep_damping[ep_itts] required");
+  if (!(ep->ep_fraction > 0.0)) return fail(NSAGP_ERR_INVALID, "ep_fraction must be positive");
+  const nsagp_model& m0 = models[0];
+  if (m0.D < 1 || m0.N < 1 || m0.N > kNP) return fail(NSAGP_ERR_INVALID, "need D >= 1 and 1 <= N <= 4 modulators");
+  if (m0.D + m0.N > 32) return fail(NSAGP_ERR_INVALID, "D + N must be <= 32 (one warp lane per latent)");
+  if (m0.bz < 1 || m0.bz > kMaxBlock || m0.bg < 1 || m0.bg > kMaxBlock)
+    return fail(NSAGP_ERR_INVALID, "block sizes must be in 1..8");
+  for (int b = 0; b < B; ++b) {
+    const nsagp_model& m = models[b];
+    if (m.D != m0.D || m.N != m0.N || m.bz != m0.bz || m.bg != m0.bg)
+      return fail(NSAGP_ERR_INVALID, "all problems of a batch must share D, N, bz, bg");
+    if (!m.A || !m.Q || !m.Pinf || !m.h) return fail(NSAGP_ERR_INVALID, "null model array");
+    const nsagp_lik& l = liks[b];
+    if (l.kind != 0 && l.kind != 1) return fail(NSAGP_ERR_INVALID, "lik.kind must be 0 or 1");
+    if (l.S < 1 || l.S != liks[0].S || !l.W || !l.wn || !l.xn)
+      return fail(NSAGP_ERR_INVALID, "likelihood tables missing or S differs within the batch");
+  }
+  return NSAGP_OK;
+}
+
+int build_lik_arrays(const nsagp_lik& l, int D, int N, int DP, std::vector<double>& W, std::vector<double>& wn,
+                     std::vector<double>& xn) {
+  W.assign((size_t)DP * kNP, 0.0);
+  for (int d = 0; d < D; ++d)
+    for (int j = 0; j < N; ++j) W[(size_t)d * kNP + j] = l.W[d + (size_t)j * D];
+  wn.assign(l.wn, l.wn + l.S);
+  xn.assign((size_t)kNP * l.S, 0.0);
+  for (int s = 0; s < l.S; ++s)
+    for (int j = 0; j < N; ++j) xn[(size_t)j * l.S + s] = l.xn[j + (size_t)s * N];
+  return NSAGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nsagp_version(void) { return "nsagp-b200 0.1 (sm_100a)"; }
+const char* nsagp_last_error(void) { return g_err.c_str(); }
+
+int nsagp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int nsagp_set_device(int device) {
+  CU(cudaSetDevice(device));
+  return NSAGP_OK;
+}
+
+int nsagp_set_stream(void* s) {
+  if (g_own_stream && g_stream) cudaStreamDestroy(g_stream);
+  g_own_stream = false;
+  g_stream = static_cast<cudaStream_t>(s);
+  return NSAGP_OK;
+}
+
+int64_t nsagp_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// ------------------------------------------------------------------ mom batch
+static int mom_batch_impl(const nsagp_lik* lik, int32_t D, int32_t N, double alpha, int64_t T, const double* y,
+                          const double* mu, const double* s2, double* lZ, double* dlZ, double* d2lZ, int warp_form) {
+  if (!lik || !y || !mu || !s2 || !lZ || !dlZ || !d2lZ) return fail(NSAGP_ERR_INVALID, "null argument");
+  if (D < 1 || N < 1 || N > kNP || D + N > 32) return fail(NSAGP_ERR_INVALID, "need 1 <= N <= 4, D + N <= 32");
+  if (lik->S < 1 || T < 0) return fail(NSAGP_ERR_INVALID, "bad S or T");
+  if (T == 0) return NSAGP_OK;
+  int rc = ensure_stream();
+  if (rc) return rc;
+  const int M = D + N, DP = (D <= 16) ? 16 : 32;
+  std::vector<double> W, wn, xn;
+  build_lik_arrays(*lik, D, N, DP, W, wn, xn);
+  DeviceArena ar;
+  MomBatchArgs a;
+  double *dW, *dwn, *dxn, *dy, *dmu, *ds2, *dl, *d1, *d2;
+  if ((rc = ar.upload(&dW, W)) || (rc = ar.upload(&dwn, wn)) || (rc = ar.upload(&dxn, xn))) { ar.release(); return rc; }
+  if ((rc = ar.alloc(&dy, T)) || (rc = ar.alloc(&dmu, T * M)) || (rc = ar.alloc(&ds2, T * M)) ||
+      (rc = ar.alloc(&dl, T)) || (rc = ar.alloc(&d1, T * M)) || (rc = ar.alloc(&d2, T * M))) { ar.release(); return rc; }
+  auto body = [&]() -> int {
+    CU(cudaMemcpyAsync(dy, y, T * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(dmu, mu, T * M * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(ds2, s2, T * M * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    a.p.D = D; a.p.N = N; a.p.S = lik->S; a.p.kind = lik->kind; a.p.sn2 = lik->sn2; a.p.shift = lik->link_shift;
+    a.p.W = dW; a.p.wn = dwn; a.p.xn = dxn;
+    a.alpha = alpha; a.T = T; a.M = M; a.y = dy; a.mu = dmu; a.s2 = ds2; a.lZ = dl; a.d1 = d1; a.d2 = d2;
+    const size_t lik_sm = ((size_t)DP * kNP + (size_t)lik->S * (1 + kNP)) * sizeof(double);
+    if (warp_form) {
+      constexpr int WPB = 4;
+      const size_t sm = lik_sm + WPB * 64 * sizeof(double);
+      const unsigned grid = (unsigned)((T + WPB - 1) / WPB);
+      if (DP == 16) mom_batch_warp_kernel<16, WPB><<<grid, 32 * WPB, sm, g_stream>>>(a);
+      else mom_batch_warp_kernel<32, WPB><<<grid, 32 * WPB, sm, g_stream>>>(a);
+    } else {
+      constexpr int TPB = 64;
+      const size_t sm = lik_sm + (size_t)4 * M * TPB * sizeof(double);
+      const unsigned grid = (unsigned)((T + TPB - 1) / TPB);
+      if (DP == 16) {
+        CU(cudaFuncSetAttribute(mom_batch_thread_kernel<16, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        mom_batch_thread_kernel<16, TPB><<<grid, TPB, sm, g_stream>>>(a);
+      } else {
+        CU(cudaFuncSetAttribute(mom_batch_thread_kernel<32, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        mom_batch_thread_kernel<32, TPB><<<grid, TPB, sm, g_stream>>>(a);
+      }
+    }
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(lZ, dl, T * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(dlZ, d1, T * M * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(d2lZ, d2, T * M * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return NSAGP_OK;
+  };
+  rc = body();
+  ar.release();
+  return rc;
+}
+
+int nsagp_mom_batch(const nsagp_lik* lik, int32_t D, int32_t N, double ep_fraction, int64_t T, const double* y,
+                    const double* mu, const double* s2, double* lZ, double* dlZ, double* d2lZ) {
+  return mom_batch_impl(lik, D, N, ep_fraction, T, y, mu, s2, lZ, dlZ, d2lZ, 0);
+}
+
+int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_fraction, int64_t T, const double* y,
+                         const double* mu, const double* s2, double* lZ, double* dlZ, double* d2lZ) {
+  return mom_batch_impl(lik, D, N, ep_fraction, T, y, mu, s2, lZ, dlZ, d2lZ, 1);
+}
+
+// ----------------------------------------------------------------------- plan
+int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsagp_model* models,
+                      const nsagp_lik* liks, const nsagp_ep* ep, const nsagp_tables* tables, const double* y,
+                      int64_t T, int32_t mode) {
+  if (!out_plan) return fail(NSAGP_ERR_INVALID, "null plan pointer");
+  *out_plan = nullptr;
+  int rc = validate_shapes(B, models, liks, ep, T);
+  if (rc) return rc;
+  if (kind != 0 && kind != 1) return fail(NSAGP_ERR_INVALID, "plan kind must be 0 (ihgp) or 1 (full-state EP)");
+  if (mode < 0 || mode > 2) return fail(NSAGP_ERR_INVALID, "bad mode");
+  if (kind == 1 && mode == NSAGP_MODE_NLZ_RUNNING) return fail(NSAGP_ERR_INVALID, "running-site mode is ihgp only");
+  if (!y) return fail(NSAGP_ERR_INVALID, "null y");
+  if (kind == 0) {
+    if (!tables) return fail(NSAGP_ERR_INVALID, "ihgp needs tables");
+    for (int b = 0; b < B; ++b) {
+      if (tables[b].nr < 2 || tables[b].nr != tables[0].nr || !tables[b].r || !tables[b].PP)
+        return fail(NSAGP_ERR_INVALID, "bad ihgp tables");
+      if (mode == NSAGP_MODE_PREDICT && !tables[b].PG) return fail(NSAGP_ERR_INVALID, "predict mode needs smoother tables PG");
+    }
+  }
+  if ((rc = ensure_stream())) return rc;
+
+  nsagp_plan* pl = new nsagp_plan();
+  pl->kind = kind; pl->B = B; pl->mode = mode; pl->T = T;
+  const nsagp_model& m0 = models[0];
+  pl->D = m0.D; pl->N = m0.N; pl->M = m0.D + m0.N; pl->bz = m0.bz; pl->bg = m0.bg;
+  pl->BM = round_bm(std::max(m0.bz, m0.bg));
+  pl->n = m0.D * m0.bz + m0.N * m0.bg;
+  pl->DP = (m0.D <= 16) ? 16 : 32;
+  pl->S = liks[0].S;
+  pl->nr = (kind == 0) ? tables[0].nr : 0;
+  pl->alpha = ep->ep_fraction;
+  pl->ep_itts = ep->ep_itts;
+  pl->damping.assign(ep->ep_damping, ep->ep_damping + ep->ep_itts);
+  const int D = pl->D, N = pl->N, M = pl->M, BM = pl->BM, nr = pl->nr, DP = pl->DP;
+  pl->PB = M * BM * BM;
+  auto bsize = [&](int i) { return i < D ? pl->bz : pl->bg; };
+
+  auto cleanup = [&](int code) {
+    pl->arena.release();
+    delete pl;
+    return code;
+  };
+
+  std::vector<int> off(M + 1, 0);
+  for (int i = 0; i < M; ++i) off[i + 1] = off[i] + bsize(i);
+  int* d_off = nullptr;
+  if ((rc = pl->arena.upload(&d_off, off))) return cleanup(rc);
+
+  pl->h_probs.resize(B);
+  pl->h_states.resize(B);
+  pl->h_vminf.assign((size_t)B * M, 0.0);
+  const bool predict = (mode == NSAGP_MODE_PREDICT);
+
+  for (int b = 0; b < B; ++b) {
+    const nsagp_model& m = models[b];
+    const nsagp_lik& l = liks[b];
+    DevProblem& P = pl->h_probs[b];
+    std::memset(&P, 0, sizeof(P));
+    P.D = D; P.N = N; P.M = M; P.BM = BM; P.n = pl->n; P.bz = pl->bz; P.bg = pl->bg;
+    P.S = l.S; P.nr = nr; P.lik_kind = l.kind; P.sn2 = l.sn2; P.link_shift = l.link_shift;
+    P.off = d_off;
+    std::vector<double> A((size_t)M * BM * BM, 0.0), Q(A.size(), 0.0), Pi(A.size(), 0.0), h((size_t)M * BM, 0.0),
+        hA((size_t)M * BM, 0.0);
+    size_t po = 0, ho = 0;
+    for (int i = 0; i < M; ++i) {
+      const int bs = bsize(i);
+      for (int c = 0; c < bs; ++c)
+        for (int r = 0; r < bs; ++r) {
+          A[(size_t)i * BM * BM + r + c * BM] = m.A[po + r + c * bs];
+          Q[(size_t)i * BM * BM + r + c * BM] = m.Q[po + r + c * bs];
+          Pi[(size_t)i * BM * BM + r + c * BM] = m.Pinf[po + r + c * bs];
+        }
+      for (int r = 0; r < bs; ++r) h[(size_t)i * BM + r] = m.h[ho + r];
+      for (int c = 0; c < bs; ++c) {
+        double s = 0.0;
+        for (int r = 0; r < bs; ++r) s += m.h[ho + r] * m.A[po + r + c * bs];
+        hA[(size_t)i * BM + c] = s;
+      }
+      po += (size_t)bs * bs; ho += bs;
+    }
+    std::vector<double> W, wn, xn;
+    build_lik_arrays(l, D, N, DP, W, wn, xn);
+    double *dA, *dQ, *dPi, *dh, *dhA, *dW, *dwn, *dxn;
+    if ((rc = pl->arena.upload(&dA, A)) || (rc = pl->arena.upload(&dQ, Q)) || (rc = pl->arena.upload(&dPi, Pi)) ||
+        (rc = pl->arena.upload(&dh, h)) || (rc = pl->arena.upload(&dhA, hA)) || (rc = pl->arena.upload(&dW, W)) ||
+        (rc = pl->arena.upload(&dwn, wn)) || (rc = pl->arena.upload(&dxn, xn)))
+      return cleanup(rc);
+    P.A = dA; P.Q = dQ; P.Pinf = dPi; P.h = dh; P.hA = dhA; P.W = dW; P.wn = dwn; P.xn = dxn;
+
+    std::vector<double> vm0(M, 0.0);
+    if (kind == 0) {
+      const nsagp_tables& tb = tables[b];
+      std::vector<double> r(tb.r, tb.r + nr), thr(nr - 1);
+      for (int i = 0; i + 1 < nr; ++i) {
+        if (!(r[i] > 0.0) || !(r[i + 1] > r[i])) return cleanup(fail(NSAGP_ERR_INVALID, "table grid r must be positive and ascending"));
+        thr[i] = bisect_threshold(r, i);
+      }
+      std::vector<double> Wtab((size_t)M * (nr + 1) * BM, 0.0), HPH((size_t)M * (nr + 1), 0.0);
+      std::vector<double> Gtab, vmtab;
+      if (tb.PG) { Gtab.assign((size_t)M * nr * BM * BM, 0.0); vmtab.assign((size_t)M * nr, 0.0); }
+      size_t ppo = 0, pgo = 0;
+      ho = 0; po = 0;
+      for (int i = 0; i < M; ++i) {
+        const int bs = bsize(i);
+        const double* hi = m.h + ho;
+        for (int row = 0; row <= nr; ++row) {
+          const double* PP = (row < nr) ? tb.PP + ppo + (size_t)row * bs * bs : m.Pinf + po;
+          double hph = 0.0;
+          for (int r_ = 0; r_ < bs; ++r_) {
+            double w = 0.0;
+            for (int c = 0; c < bs; ++c) w += PP[r_ + c * bs] * hi[c];     // W = PP*h'
+            Wtab[((size_t)i * (nr + 1) + row) * BM + r_] = w;
+          }
+          for (int r_ = 0; r_ < bs; ++r_) hph += hi[r_] * Wtab[((size_t)i * (nr + 1) + row) * BM + r_];
+          HPH[(size_t)i * (nr + 1) + row] = hph;
+        }
+        vm0[i] = HPH[(size_t)i * (nr + 1) + nr];
+        if (tb.PG) {
+          for (int row = 0; row < nr; ++row) {
+            const double* Ps = tb.PG + pgo + (size_t)row * 2 * bs * bs;
+            const double* G = Ps + bs * bs;
+            for (int c = 0; c < bs; ++c)
+              for (int r_ = 0; r_ < bs; ++r_) Gtab[((size_t)i * nr + row) * BM * BM + r_ + c * BM] = G[r_ + c * bs];
+            double v = 0.0;
+            for (int c = 0; c < bs; ++c) {
+              double hp = 0.0;
+              for (int r_ = 0; r_ < bs; ++r_) hp += hi[r_] * Ps[r_ + c * bs];   // (h*P)
+              v += hp * hi[c];
+            }
+            vmtab[(size_t)i * nr + row] = v;
+          }
+          pgo += (size_t)nr * 2 * bs * bs;
+        }
+        ppo += (size_t)nr * bs * bs; po += (size_t)bs * bs; ho += bs;
+      }
+      double *dr, *dthr, *dWt, *dHPH, *dG = nullptr, *dvm = nullptr;
+      if ((rc = pl->arena.upload(&dr, r)) || (rc = pl->arena.upload(&dthr, thr)) || (rc = pl->arena.upload(&dWt, Wtab)) ||
+          (rc = pl->arena.upload(&dHPH, HPH)))
+        return cleanup(rc);
+      if (tb.PG && ((rc = pl->arena.upload(&dG, Gtab)) || (rc = pl->arena.upload(&dvm, vmtab)))) return cleanup(rc);
+      P.r = dr; P.thr = dthr; P.Wtab = dWt; P.HPHtab = dHPH; P.Gtab = dG; P.vmtab = dvm;
+    } else {
+      ho = 0; po = 0;
+      for (int i = 0; i < M; ++i) {
+        const int bs = bsize(i);
+        double v = 0.0;
+        for (int c = 0; c < bs; ++c) {
+          double hp = 0.0;
+          for (int r_ = 0; r_ < bs; ++r_) hp += m.h[ho + r_] * m.Pinf[po + r_ + c * bs];
+          v += hp * m.h[ho + c];
+        }
+        vm0[i] = v;
+        po += (size_t)bs * bs; ho += bs;
+      }
+    }
+    for (int i = 0; i < M; ++i) pl->h_vminf[(size_t)b * M + i] = vm0[i];
+
+    DevState& St = pl->h_states[b];
+    std::memset(&St, 0, sizeof(St));
+    double *dy, *dtt, *dtn, *dR, *dMS, *dE, *dlZ, *dmc, *dvm0, *dV = nullptr, *dPS = nullptr;
+    unsigned long long *dmax, *dneg;
+    int* dstat;
+    if ((rc = pl->arena.alloc(&dy, T)) || (rc = pl->arena.alloc(&dtt, T * M)) || (rc = pl->arena.alloc(&dtn, T * M)) ||
+        (rc = pl->arena.alloc(&dR, T * M)) || (rc = pl->arena.alloc(&dMS, T * pl->n)) ||
+        (rc = pl->arena.alloc(&dE, T * M)) || (rc = pl->arena.alloc(&dlZ, T)) ||
+        (rc = pl->arena.alloc(&dmc, (size_t)M * BM)) || (rc = pl->arena.upload(&dvm0, vm0)) ||
+        (rc = pl->arena.alloc(&dmax, 2)) || (rc = pl->arena.alloc(&dneg, 1)) || (rc = pl->arena.alloc(&dstat, 1)))
+      return cleanup(rc);
+    if (kind == 1) {
+      if ((rc = pl->arena.alloc(&dV, T * M)) || (rc = pl->arena.alloc(&dPS, (size_t)T * pl->PB))) return cleanup(rc);
+    }
+    St.y = dy; St.ttau = dtt; St.tnu = dtn; St.R = dR; St.MS = dMS; St.E = dE; St.V = dV; St.lZ = dlZ; St.PS = dPS;
+    St.mcarry = dmc; St.vm0 = dvm0; St.maxdiff = dmax; St.negcav = dneg; St.status = dstat;
+    cudaError_t e = cudaMemcpy(dy, y + (size_t)b * T, T * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cleanup(fail(NSAGP_ERR_CUDA, std::string("upload y: ") + cudaGetErrorString(e)));
+  }
+  if ((rc = pl->arena.upload(&pl->d_probs, pl->h_probs)) || (rc = pl->arena.upload(&pl->d_states, pl->h_states)))
+    return cleanup(rc);
+  const long long nchunks = (T + kScanChunk - 1) / kScanChunk;
+  const size_t per_chunk = (kind == 0) ? (size_t)(BM * BM + BM) : (size_t)(2 * BM * BM + BM);
+  if ((rc = pl->arena.alloc(&pl->d_chunk, (size_t)B * nchunks * M * per_chunk)) ||
+      (rc = pl->arena.alloc(&pl->d_start, (size_t)B * nchunks * M * (kind == 0 ? BM : BM * BM + BM))) ||
+      (rc = pl->arena.alloc(&pl->d_nlZ, (size_t)B * (pl->ep_itts + 1))) ||
+      (rc = pl->arena.alloc(&pl->d_diag, (size_t)B * pl->ep_itts * 2)))
+    return cleanup(rc);
+  if (predict) {
+    if ((rc = pl->arena.alloc(&pl->d_MF, (size_t)B * T * pl->n))) return cleanup(rc);
+    if (kind == 1 && (rc = pl->arena.alloc(&pl->d_PF, (size_t)B * T * pl->PB))) return cleanup(rc);
+  }
+  cudaEventCreate(&pl->ev[0]);
+  cudaEventCreate(&pl->ev[1]);
+  *out_plan = pl;
+  return NSAGP_OK;
+}
+
+int nsagp_plan_destroy(nsagp_plan* pl) {
+  if (!pl) return NSAGP_OK;
+  pl->arena.release();
+  if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
+  if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
+  for (cudaEvent_t e : pl->phase_ev) cudaEventDestroy(e);
+  delete pl;
+  return NSAGP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------ run: dispatch
+namespace {
+
+// (variadic: the bodies contain commas, e.g. in <<<...>>>)
+#define DISPATCH_BM(BMV, ...)                                             \
+  switch (BMV) {                                                          \
+    case 2: { constexpr int BM_ = 2; __VA_ARGS__; } break;                \
+    case 3: { constexpr int BM_ = 3; __VA_ARGS__; } break;                \
+    case 4: { constexpr int BM_ = 4; __VA_ARGS__; } break;                \
+    case 6: { constexpr int BM_ = 6; __VA_ARGS__; } break;                \
+    default: { constexpr int BM_ = 8; __VA_ARGS__; } break;               \
+  }
+
+#define DISPATCH_DP(DPV, ...)                                             \
+  if ((DPV) == 16) { constexpr int DP_ = 16; __VA_ARGS__; } else { constexpr int DP_ = 32; __VA_ARGS__; }
+
+struct PhaseTimer {
+  nsagp_plan* pl;
+  // pairs of events with a phase id
+  std::vector<int> ids;
+  size_t used = 0;
+  int begin(int id) {
+    if (used + 2 > pl->phase_ev.size()) {
+      cudaEvent_t a, b;
+      CU(cudaEventCreate(&a));
+      CU(cudaEventCreate(&b));
+      pl->phase_ev.push_back(a);
+      pl->phase_ev.push_back(b);
+    }
+    ids.push_back(id);
+    CU(cudaEventRecord(pl->phase_ev[used], g_stream));
+    return NSAGP_OK;
+  }
+  int end() {
+    CU(cudaEventRecord(pl->phase_ev[used + 1], g_stream));
+    used += 2;
+    return NSAGP_OK;
+  }
+  int collect() {
+    for (int i = 1; i < 5; ++i) pl->timings[i] = 0.0;
+    for (size_t i = 0; i < ids.size(); ++i) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, pl->phase_ev[2 * i], pl->phase_ev[2 * i + 1]));
+      pl->timings[ids[i]] += ms;
+    }
+    return NSAGP_OK;
+  }
+};
+
+size_t lik_smem_bytes(const nsagp_plan* pl) {
+  return ((size_t)pl->DP * kNP + (size_t)pl->S * (1 + kNP)) * sizeof(double);
+}
+
+int launch_sum(nsagp_plan* pl, int slot, int neg) {
+  sum_kernel<<<pl->B, 1024, 0, g_stream>>>(pl->d_states, pl->T, pl->d_nlZ, pl->ep_itts + 1, slot, neg);
+  LAUNCH_CHECK();
+  return NSAGP_OK;
+}
+
+int reset_diag(nsagp_plan* pl) {
+  for (int b = 0; b < pl->B; ++b) CU(cudaMemsetAsync(pl->h_states[b].maxdiff, 0, 16, g_stream));
+  return NSAGP_OK;
+}
+
+int save_diag(nsagp_plan* pl, int itt) {
+  for (int b = 0; b < pl->B; ++b)
+    CU(cudaMemcpyAsync(pl->d_diag + ((size_t)b * pl->ep_itts + itt) * 2, pl->h_states[b].maxdiff, 16,
+                       cudaMemcpyDeviceToDevice, g_stream));
+  return NSAGP_OK;
+}
+
+int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double damp, int running) {
+  const size_t sm = 64 * sizeof(double) + lik_smem_bytes(pl);
+  DISPATCH_DP(pl->DP, DISPATCH_BM(pl->BM, {
+    auto kern = ihgp_adf_kernel<DP_, BM_>;
+    if (sm > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<pl->B, 32, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
+  }));
+  LAUNCH_CHECK();
+  return NSAGP_OK;
+}
+
+template <template <int> class ElemT, int DIR>
+int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int init, long long kinit) {
+  if (nsteps <= 0) return NSAGP_OK;
+  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
+  constexpr int CH = 4;
+  const dim3 block(32, CH);
+  const dim3 grid((unsigned)((nchunks + CH - 1) / CH), pl->B);
+  DISPATCH_BM(pl->BM, {
+    affine_reduce_kernel<BM_, ElemT<BM_>, DIR><<<grid, block, 0, g_stream>>>(pl->d_probs, pl->d_states, kfirst, nsteps, pl->d_chunk);
+    LAUNCH_CHECK();
+    affine_carry_kernel<BM_><<<pl->B, 32, 0, g_stream>>>(pl->d_probs, pl->d_states, nsteps, init, kinit, pl->d_chunk, pl->d_start);
+    LAUNCH_CHECK();
+    affine_apply_kernel<BM_, ElemT<BM_>, DIR><<<grid, block, 0, g_stream>>>(pl->d_probs, pl->d_states, kfirst, nsteps, pl->d_start);
+    LAUNCH_CHECK();
+  });
+  return NSAGP_OK;
+}
+
+int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ) {
+  if (pl->T < 2) return NSAGP_OK;
+  constexpr int TPB = 64;
+  const size_t sm = (size_t)4 * pl->M * TPB * sizeof(double) + lik_smem_bytes(pl);
+  const dim3 grid((unsigned)((pl->T - 1 + TPB - 1) / TPB), pl->B);
+  DISPATCH_DP(pl->DP, {
+    auto kern = ihgp_site_update_kernel<DP_, TPB>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, pl->alpha, damp, write_lZ);
+  });
+  LAUNCH_CHECK();
+  return NSAGP_OK;
+}
+
+int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
+  const long long T = pl->T;
+  int rc;
+  if (pl->mode != NSAGP_MODE_PREDICT) {
+    // nlZ mode: a single ADF sweep (ihgp_ep_modulator_nmf.m:533-624)
+    if ((rc = tm.begin(1))) return rc;
+    if ((rc = ihgp_adf(pl, 0, T, 1, pl->damping[0], pl->mode == NSAGP_MODE_NLZ_RUNNING))) return rc;
+    if ((rc = tm.end())) return rc;
+    return launch_sum(pl, pl->ep_itts, 1);
+  }
+  double damp = pl->damping[0];
+  for (int itt = 1; itt <= pl->ep_itts; ++itt) {
+    if ((rc = reset_diag(pl))) return rc;
+    if (itt == 1) {
+      if ((rc = tm.begin(1)) || (rc = ihgp_adf(pl, 0, T, 1, damp, 0)) || (rc = tm.end())) return rc;
+      if ((rc = launch_sum(pl, 0, 1))) return rc;
+    } else {
+      if ((rc = tm.begin(2))) return rc;
+      if ((rc = affine_scan<FilterElem, +1>(pl, 0, T - 1, 0, 0))) return rc;
+      if ((rc = ihgp_adf(pl, T - 1, T, 0, damp, 0))) return rc;     // last step: moments + update (:253)
+      if ((rc = tm.end())) return rc;
+    }
+    if (itt == pl->ep_itts && pl->d_MF) {
+      for (int b = 0; b < pl->B; ++b)
+        CU(cudaMemcpyAsync(pl->d_MF + (size_t)b * T * pl->n, pl->h_states[b].MS, (size_t)T * pl->n * sizeof(double),
+                           cudaMemcpyDeviceToDevice, g_stream));
+    }
+    if (itt < pl->ep_itts) damp = pl->damping[itt];                 // ep_damping(itt+1) (:369-371)
+    if ((rc = tm.begin(3))) return rc;
+    if ((rc = affine_scan<SmootherElem, -1>(pl, T - 2, T - 1, 1, T - 1))) return rc;
+    if ((rc = tm.end())) return rc;
+    if (itt < pl->ep_itts) {
+      if ((rc = tm.begin(4)) || (rc = ihgp_site_update(pl, damp, itt > 1)) || (rc = tm.end())) return rc;
+      if ((rc = launch_sum(pl, itt, 1))) return rc;
+      DISPATCH_BM(pl->BM, { carry_mean_kernel<BM_><<<pl->B, 32, 0, g_stream>>>(pl->d_probs, pl->d_states); });
+      LAUNCH_CHECK();
+    }
+    if ((rc = save_diag(pl, itt - 1))) return rc;
+  }
+  return NSAGP_OK;
+}
+
+}  // namespace
+
+#include "api_full.inc"
+
+extern "C" {
+
+int nsagp_plan_run(nsagp_plan* pl) {
+  if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
+  int rc = ensure_stream();
+  if (rc) return rc;
+  // (re)initialise the mutable state so a plan can be run repeatedly
+  const long long T = pl->T;
+  for (int b = 0; b < pl->B; ++b) {
+    DevState& St = pl->h_states[b];
+    CU(cudaMemsetAsync(St.ttau, 0, (size_t)T * pl->M * 8, g_stream));
+    CU(cudaMemsetAsync(St.tnu, 0, (size_t)T * pl->M * 8, g_stream));
+    CU(cudaMemsetAsync(St.R, 0, (size_t)T * pl->M * 8, g_stream));
+    CU(cudaMemsetAsync(St.MS, 0, (size_t)T * pl->n * 8, g_stream));
+    CU(cudaMemsetAsync(St.E, 0, (size_t)T * pl->M * 8, g_stream));
+    CU(cudaMemsetAsync(St.lZ, 0, (size_t)T * 8, g_stream));
+    CU(cudaMemsetAsync(St.mcarry, 0, (size_t)pl->M * pl->BM * 8, g_stream));
+    CU(cudaMemsetAsync(St.maxdiff, 0, 16, g_stream));
+    CU(cudaMemsetAsync(St.negcav, 0, 8, g_stream));
+    CU(cudaMemsetAsync(St.status, 0, 4, g_stream));
+    if (St.V) CU(cudaMemsetAsync(St.V, 0, (size_t)T * pl->M * 8, g_stream));
+    CU(cudaMemcpyAsync(St.vm0, pl->h_vminf.data() + (size_t)b * pl->M, pl->M * 8, cudaMemcpyHostToDevice, g_stream));
+  }
+  CU(cudaMemsetAsync(pl->d_nlZ, 0, (size_t)pl->B * (pl->ep_itts + 1) * 8, g_stream));
+  CU(cudaMemsetAsync(pl->d_diag, 0, (size_t)pl->B * pl->ep_itts * 16, g_stream));
+  PhaseTimer tm{pl};
+  CU(cudaEventRecord(pl->ev[0], g_stream));
+  rc = (pl->kind == 0) ? run_ihgp(pl, tm) : run_full(pl, tm);
+  if (rc) return rc;
+  CU(cudaEventRecord(pl->ev[1], g_stream));
+  CU(cudaStreamSynchronize(g_stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]));
+  pl->timings[0] = ms;
+  if ((rc = tm.collect())) return rc;
+  pl->ran = true;
+  // sticky device-side status (full-state path: Cholesky failure / non-positive variance)
+  for (int b = 0; b < pl->B; ++b) {
+    int st = 0;
+    CU(cudaMemcpy(&st, pl->h_states[b].status, 4, cudaMemcpyDeviceToHost));
+    if (st == 1) return fail(NSAGP_ERR_NOT_PD, "smoother Cholesky failed (predicted covariance not positive definite)");
+    if (st == 2) return fail(NSAGP_ERR_NONPOS_VAR, "non-positive predictive variance in nlZ mode");
+  }
+  return NSAGP_OK;
+}
+
+int nsagp_plan_timings(nsagp_plan* pl, double* ms, int32_t n) {
+  if (!pl || !ms) return 0;
+  const int k = std::min<int>(n, 5);
+  for (int i = 0; i < k; ++i) ms[i] = pl->timings[i];
+  return k;
+}
+
+int nsagp_plan_fetch(nsagp_plan* pl, int32_t b, nsagp_outputs* o) {
+  if (!pl || !o) return fail(NSAGP_ERR_INVALID, "null argument");
+  if (!pl->ran) return fail(NSAGP_ERR_INVALID, "plan has not been run");
+  if (b < 0 || b >= pl->B) return fail(NSAGP_ERR_INVALID, "problem index out of range");
+  const DevState& St = pl->h_states[b];
+  const long long T = pl->T;
+  const int M = pl->M;
+  const size_t TM = (size_t)T * M * 8;
+  auto get = [&](void* dst, const void* src, size_t nb) -> int {
+    if (!dst) return NSAGP_OK;
+    if (!src) return fail(NSAGP_ERR_INVALID, "requested output is not produced in this mode");
+    CU(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDeviceToHost, g_stream));
+    return NSAGP_OK;
+  };
+  int rc;
+  const bool predict = pl->mode == NSAGP_MODE_PREDICT;
+  if ((rc = get(o->ttau, St.ttau, TM)) || (rc = get(o->tnu, St.tnu, TM)) || (rc = get(o->R, St.R, TM)) ||
+      (rc = get(o->lZ, St.lZ, (size_t)T * 8)))
+    return rc;
+  if (predict) {
+    if ((rc = get(o->Eft, St.E, TM)) || (rc = get(o->MS, St.MS, (size_t)T * pl->n * 8)) ||
+        (rc = get(o->MF, pl->d_MF ? pl->d_MF + (size_t)b * T * pl->n : nullptr, (size_t)T * pl->n * 8)))
+      return rc;
+    if (pl->kind == 1) {
+      if ((rc = get(o->Varft, St.V, TM))) return rc;
+      if ((rc = fetch_full_cov(pl, b, o))) return rc;
+    }
+    if ((rc = get(o->nlZ, pl->d_nlZ + (size_t)b * (pl->ep_itts + 1), (size_t)pl->ep_itts * 8))) return rc;
+  } else {
+    if (o->Eft || o->Varft || o->lb || o->ub || o->MS || o->MF || o->PF || o->PS)
+      return fail(NSAGP_ERR_INVALID, "posterior outputs are only available in predict mode");
+  }
+  if ((rc = get(o->edata, pl->d_nlZ + (size_t)b * (pl->ep_itts + 1) + pl->ep_itts, 8))) return rc;
+  std::vector<double> diag;
+  if (o->maxDiffM || o->maxDiffP) {
+    diag.resize((size_t)pl->ep_itts * 2);
+    CU(cudaMemcpyAsync(diag.data(), pl->d_diag + (size_t)b * pl->ep_itts * 2, diag.size() * 8, cudaMemcpyDeviceToHost, g_stream));
+  }
+  unsigned long long neg = 0;
+  if (o->n_negcav) CU(cudaMemcpyAsync(&neg, St.negcav, 8, cudaMemcpyDeviceToHost, g_stream));
+  std::vector<double> vm0;
+  if (predict && pl->kind == 0 && (o->Varft || o->lb || o->ub)) {
+    vm0.resize(M);
+    CU(cudaMemcpyAsync(vm0.data(), St.vm0, M * 8, cudaMemcpyDeviceToHost, g_stream));
+  }
+  CU(cudaStreamSynchronize(g_stream));
+  if (o->n_negcav) *o->n_negcav = (int64_t)neg;
+  for (int i = 0; i < pl->ep_itts && !diag.empty(); ++i) {
+    if (o->maxDiffM) o->maxDiffM[i] = diag[2 * i];
+    if (o->maxDiffP) o->maxDiffP[i] = diag[2 * i + 1];
+  }
+  if (predict && pl->kind == 0) {
+    // Varft: one M-vector (marginal variance of the last look-up) replicated over
+    // time, abs() as in ihgp_ep_modulator_nmf.m:492-496
+    if (o->Varft)
+      for (long long k = 0; k < T; ++k)
+        for (int i = 0; i < M; ++i) o->Varft[k * M + i] = std::fabs(vm0[i]);
+  }
+  if (predict && (o->lb || o->ub)) {
+    // lb/ub = Eft -/+ 1.96 sqrt(Varft)  (gf_ep_modulator_nmf.m:346-347)
+    std::vector<double> Etmp, Vtmp;
+    const double* E = o->Eft;
+    const double* V = o->Varft;
+    if (!E) { Etmp.resize((size_t)T * M); CU(cudaMemcpy(Etmp.data(), St.E, TM, cudaMemcpyDeviceToHost)); E = Etmp.data(); }
+    if (!V) {
+      Vtmp.resize((size_t)T * M);
+      if (pl->kind == 0) { for (long long k = 0; k < T; ++k) for (int i = 0; i < M; ++i) Vtmp[k * M + i] = std::fabs(vm0[i]); }
+      else CU(cudaMemcpy(Vtmp.data(), St.V, TM, cudaMemcpyDeviceToHost));
+      V = Vtmp.data();
+    }
+    for (size_t i = 0; i < (size_t)T * M; ++i) {
+      const double sd = 1.96 * std::sqrt(V[i]);
+      if (o->lb) o->lb[i] = E[i] - sd;
+      if (o->ub) o->ub[i] = E[i] + sd;
+    }
+  }
+  return NSAGP_OK;
+}
+
+static int run_hostbuf(int kind, int32_t B, const nsagp_model* models, const nsagp_lik* liks, const nsagp_ep* ep,
+                       const nsagp_tables* tables, const double* y, int64_t T, int32_t mode, nsagp_outputs* outs) {
+  if (!outs) return fail(NSAGP_ERR_INVALID, "null outputs");
+  nsagp_plan* pl = nullptr;
+  int rc = nsagp_plan_create(&pl, kind, B, models, liks, ep, tables, y, T, mode);
+  if (rc) return rc;
+  rc = nsagp_plan_run(pl);
+  for (int b = 0; b < B && !rc; ++b) rc = nsagp_plan_fetch(pl, b, &outs[b]);
+  nsagp_plan_destroy(pl);
+  return rc;
+}
+
+int nsagp_ep_ihgp(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep, const nsagp_tables* tables,
+                  const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
+  return run_hostbuf(0, 1, model, lik, ep, tables, y, T, mode, out);
+}
+
+int nsagp_ep_ihgp_batch(int32_t B, const nsagp_model* models, const nsagp_lik* liks, const nsagp_ep* ep,
+                        const nsagp_tables* tables, const double* y, int64_t T, int32_t mode, nsagp_outputs* outs) {
+  return run_hostbuf(0, B, models, liks, ep, tables, y, T, mode, outs);
+}
+
+int nsagp_ep_full(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep, const double* y, int64_t T,
+                  int32_t mode, nsagp_outputs* out) {
+  return run_hostbuf(1, 1, model, lik, ep, nullptr, y, T, mode, out);
+}
+
+int nsagp_ep_full_batch(int32_t B, const nsagp_model* models, const nsagp_lik* liks, const nsagp_ep* ep,
+                        const double* y, int64_t T, int32_t mode, nsagp_outputs* outs) {
+  return run_hostbuf(1, B, models, liks, ep, nullptr, y, T, mode, outs);
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+"""Entry points with the reference's own names, argument order and return values.
+
+    gf_ep_modulator_nmf                  matlab/gf_ep_modulator_nmf.m:1
+    gf_ep_modulator_nmf_constraints      matlab/gf_ep_modulator_nmf_constraints.m:1
+    ihgp_ep_modulator_nmf                matlab/ihgp_ep_modulator_nmf.m:1
+    ihgp_ep_modulator_nmf_constraints    matlab/ihgp_ep_modulator_nmf_constraints.m:1
+
+Same parameter vectors in; ``(nlZ, grad)`` (xt empty) or
+``(Eft, Varft, Covft, lb, ub, out)`` (xt given) out.  Host work is limited to
+what the reference also does once per call with MATLAB built-ins (unpacking,
+``ss``, ``balance``, ``lti_disc``, DARE tables); the time loops run in the CUDA
+library through the C ABI (include/nsagp.h).  Indices are 0-based.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, ssmodel, tables as tables_mod
+from .lik import Moments
+
+
+# --------------------------------------------------------------------- helpers
+def merge_inputs(x, y, xt):
+    """Combine observations and test points, sort, de-duplicate keeping the first
+    occurrence; test-only points carry NaN (gf_ep_modulator_nmf.m:58-66)."""
+    x = np.asarray(x, float).ravel()
+    y = np.asarray(y, float).ravel()
+    if x.size != y.size:
+        raise ValueError("x and y must have the same number of elements")
+    xt = np.zeros(0) if xt is None else np.asarray(xt, float).ravel()
+    xall = np.concatenate([x, xt])
+    yall = np.concatenate([y, np.full(xt.size, np.nan)])
+    _, first, inverse = np.unique(xall, return_index=True, return_inverse=True)
+    return yall[first], inverse[xall.size - xt.size:]
+
+
+def sigmoid(x, sig_range=(0.0, 20.0), c=0.0, a=1.0):
+    """matlab/sigmoid.m:17-19."""
+    lo, up = float(sig_range[0]), float(sig_range[-1])
+    return (up - lo) / (1.0 + np.exp(-a * (np.asarray(x, float) - c))) + lo
+
+
+def inv_sigmoid(y, sig_range=(0.0, 20.0), c=0.0, a=1.0):
+    """matlab/inv_sigmoid.m:17-23."""
+    lo, up = float(sig_range[0]), float(sig_range[-1])
+    y = np.asarray(y, float)
+    ratio = (up - y) / (y - lo)
+    if np.any(~(ratio > 0)):
+        raise ValueError("Error with inverse sigmoid transformation: parameter outside of user specified range")
+    return c - np.log(ratio) / a
+
+
+def lambda_map(lin, kernel):
+    """matlab/lambda_map.m."""
+    c = {"exp": 1.0, "matern32": 3.0 ** 0.5, "matern52": 5.0 ** 0.5, "matern72": 7.0 ** 0.5}[kernel]
+    return c / np.asarray(lin, float)
+
+
+def _unpack_log(w, nlik, D, N):
+    w = np.asarray(w, float).ravel()
+    need = nlik + 3 * D + 2 * N + D * N
+    if w.size != need:
+        raise ValueError("w has %d entries, expected %d" % (w.size, need))
+    e = np.exp(w[nlik:])
+    return w[:nlik], e[:3 * D], e[3 * D:3 * D + 2 * N], e[3 * D + 2 * N:].reshape((D, N), order="F")
+
+
+def _unpack_constrained(w, nlik, D, N, constraints, w_fixed, tune_hypers):
+    """Split tuned / fixed parameters and squash them into their boxes
+    (gf_ep_modulator_nmf_constraints.m:75-110)."""
+    src = {True: [np.asarray(w, float).ravel(), 0], False: [np.asarray(w_fixed, float).ravel(), 0]}
+    cons = np.asarray(constraints, float)
+    tune = [bool(t) for t in np.asarray(tune_hypers).ravel()]
+
+    def take(flag, count):
+        arr, pos = src[flag]
+        src[flag][1] = pos + count
+        return arr[pos:pos + count]
+
+    lik_param = take(tune[0], nlik)
+    groups = [sigmoid(take(tune[i], D if i <= 3 else N), cons[i - 1]) for i in range(1, 6)]
+    arr, pos = src[tune[6]]
+    Wnmf = sigmoid(arr[pos:], cons[5]).reshape((D, N), order="F")
+    return lik_param, np.concatenate(groups[:3]), np.concatenate(groups[3:]), Wnmf
+
+
+def _discrete_model(ss, x, param1, param2, kernel1, kernel2, D, N, balance, symmetrise_Q):
+    F, L, Qc, H, Pinf = ss(x, param1, param2, kernel1, kernel2)[:5]
+    if balance:
+        F, L, H, Pinf = ssmodel.balance(F, L, H, Pinf)
+    A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)              # dt = 1 is hard-coded in the reference
+    if symmetrise_Q:
+        Q = (Q + Q.T) / 2                               # ihgp_ep_modulator_nmf.m:97
+    return ssmodel.to_block_model(A, Q, H, Pinf, D, N), H
+
+
+def _require_moments(mom):
+    if not isinstance(mom, Moments):
+        raise TypeError("`mom` must be built with likModulatorNMFPower(...) or likModulatorPreCalcwn(...): "
+                        "an arbitrary function handle cannot run on the GPU")
+    return mom
+
+
+# ------------------------------------------------------------------------ plan
+class Plan:
+    """Device-resident EP problem(s): thin wrapper over nsagp_plan_* (include/nsagp.h).
+
+    models: list of ssmodel.BlockModel; liks: list of (Moments, lik_param, W);
+    y: (B, T) array (NaN = missing); tables: list of tables.IhgpTables for kind 0."""
+
+    def __init__(self, kind, models, liks, ep_fraction, ep_damping, ep_itts, y, mode, tables=None):
+        L = _lib.lib()
+        self.kind, self.mode = kind, mode
+        self.B = len(models)
+        y = _lib.as_f64(np.atleast_2d(y))
+        if y.shape[0] != self.B:
+            raise ValueError("y must have one row per problem")
+        self.T = y.shape[1]
+        self.models = models
+        self.ep_itts = int(ep_itts)
+        damping = _lib.as_f64(np.atleast_1d(ep_damping).ravel())
+        if damping.size < self.ep_itts:
+            raise ValueError("ep_damping must have at least ep_itts entries (it is indexed by itt+1)")
+        keep = [y, damping]
+        cm = (_lib.Model * self.B)()
+        cl = (_lib.Lik * self.B)()
+        ct = (_lib.Tables * self.B)() if kind == _lib.KIND_IHGP else None
+        for b, (mdl, (mom, lik_param, W)) in enumerate(zip(models, liks)):
+            arrs = [_lib.as_f64(a) for a in (mdl.A, mdl.Q, mdl.Pinf, mdl.h)]
+            keep.extend(arrs)
+            cm[b].D, cm[b].N, cm[b].bz, cm[b].bg = mdl.D, mdl.N, mdl.bz, mdl.bg
+            cm[b].A, cm[b].Q, cm[b].Pinf, cm[b].h = [_lib.dptr(a) for a in arrs]
+            cl[b] = _require_moments(mom).c_lik(lik_param, W, keep)
+            if ct is not None:
+                tb = tables[b]
+                pp, pg = tb.packed()
+                r = _lib.as_f64(tb.r); pp = _lib.as_f64(pp)
+                keep.extend([r, pp])
+                ct[b].nr = r.size; ct[b].r = _lib.dptr(r); ct[b].PP = _lib.dptr(pp)
+                if pg is not None:
+                    pg = _lib.as_f64(pg); keep.append(pg)
+                    ct[b].PG = _lib.dptr(pg)
+        ep = _lib.Ep(float(ep_fraction), _lib.dptr(damping), self.ep_itts)
+        self._h = C.c_void_p()
+        _lib.check(L.nsagp_plan_create(C.byref(self._h), kind, self.B, cm, cl, C.byref(ep), ct,
+                                       _lib.dptr(y), self.T, mode))
+        self._keep = keep
+
+    def run(self):
+        _lib.check(_lib.lib().nsagp_plan_run(self._h))
+        return self
+
+    def timings(self):
+        ms = np.zeros(5)
+        _lib.lib().nsagp_plan_timings(self._h, _lib.dptr(ms), 5)
+        return dict(total=ms[0], adf=ms[1], fixed_filter=ms[2], smoother=ms[3], site_update=ms[4])
+
+    def fetch(self, b=0, names=("Eft", "Varft", "lb", "ub")):
+        """Copy the named outputs of problem b to the host.  M-by-T / n-by-T arrays
+        come back in MATLAB orientation (sites or states along axis 0)."""
+        mdl = self.models[b]
+        M, n, T = mdl.M, mdl.n, self.T
+        nb = mdl.D * mdl.bz ** 2 + mdl.N * mdl.bg ** 2
+        shapes = dict(Eft=(T, M), Varft=(T, M), lb=(T, M), ub=(T, M), ttau=(T, M), tnu=(T, M), R=(T, M), lZ=(T,),
+                      MF=(T, n), MS=(T, n), PF=(T, nb), PS=(T, nb), nlZ=(self.ep_itts,),
+                      maxDiffM=(self.ep_itts,), maxDiffP=(self.ep_itts,), edata=(1,))
+        o = _lib.Outputs()
+        bufs = {}
+        for nm in names:
+            if nm == "n_negcav":
+                bufs[nm] = np.zeros(1, np.int64)
+                o.n_negcav = bufs[nm].ctypes.data_as(C.POINTER(C.c_int64))
+            else:
+                bufs[nm] = np.empty(shapes[nm])
+                setattr(o, nm, _lib.dptr(bufs[nm]))
+        _lib.check(_lib.lib().nsagp_plan_fetch(self._h, b, C.byref(o)))
+        out = {}
+        for nm, a in bufs.items():
+            if nm == "n_negcav":
+                out[nm] = int(a[0])
+            elif nm == "edata":
+                out[nm] = float(a[0])
+            else:
+                out[nm] = a.T if a.ndim == 2 else a
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.lib().nsagp_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_DEBUG = ("tnu", "ttau", "lZ", "R", "MF", "MS", "nlZ", "maxDiffM", "maxDiffP", "n_negcav")
+
+
+def _predict_outputs(plan, mdl, return_ind, nargout, debug_cov):
+    names = ["Eft"]
+    if nargout > 1:
+        names.append("Varft")
+    if nargout > 3:
+        names += ["lb", "ub"]
+    if nargout > 5:
+        names += list(_DEBUG)
+        if debug_cov and plan.kind == _lib.KIND_FULL:
+            names += ["PF", "PS"]
+    res = plan.fetch(0, names)
+    sel = lambda a: a[:, return_ind]
+    Eft = sel(res["Eft"])
+    if nargout <= 1:
+        return (Eft,)
+    Varft = sel(res["Varft"])
+    if nargout <= 3:
+        return Eft, Varft
+    lb, ub = sel(res["lb"]), sel(res["ub"])
+    if nargout <= 5:
+        return Eft, Varft, None, lb, ub
+    out = {k: res[k] for k in _DEBUG}
+    for k in ("PF", "PS"):
+        if k in res:
+            out[k] = res[k]              # packed per-block covariances, (sum b^2)-by-T
+    return Eft, Varft, None, lb, ub, out
+
+
+def _run(kind, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction, ep_damping, ep_itts,
+         constrained, balance, nargout, debug_cov, nlz_mode=_lib.MODE_NLZ):
+    mom = _require_moments(mom)
+    yall, return_ind = merge_inputs(x, y, xt)
+    if constrained is None:
+        lik_param, param1, param2, Wnmf = _unpack_log(w, num_lik_params, D, N)
+    else:
+        lik_param, param1, param2, Wnmf = _unpack_constrained(w, num_lik_params, D, N, *constrained)
+    mdl, _ = _discrete_model(ss, x, param1, param2, kernel1, kernel2, D, N, balance,
+                             symmetrise_Q=(kind == _lib.KIND_IHGP))
+    predict = xt is not None and np.size(xt) > 0
+    tabs = None
+    if kind == _lib.KIND_IHGP:
+        tabs = [tables_mod.build_tables(mdl, want_smoother=predict)]
+    mode = _lib.MODE_PREDICT if predict else nlz_mode
+    with Plan(kind, [mdl], [(mom, lik_param, Wnmf)], ep_fraction, ep_damping, ep_itts, yall[None, :], mode,
+              tables=tabs) as plan:
+        plan.run()
+        if predict:
+            res = _predict_outputs(plan, mdl, return_ind, nargout, debug_cov)
+            if nargout > 5 and tabs is not None:
+                res[5].update(r=tabs[0].r, ro=tabs[0].ro, PPlist=tabs[0].PP)     # ihgp_ep_modulator_nmf.m:137-141
+            return res
+        edata = plan.fetch(0, ("edata",))["edata"]
+    # the reference returns an all-zero gradient (gf_ep_modulator_nmf.m:363,531)
+    return edata, np.zeros(np.size(w))
+
+
+# ---------------------------------------------------------------- entry points
+def gf_ep_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
+                        ep_fraction, ep_damping, ep_itts, nargout=6, debug_cov=False):
+    """Solve the time-frequency-NMF GP model by Power EP (full-state Kalman filter /
+    RTS smoother).  Drop-in for matlab/gf_ep_modulator_nmf.m."""
+    return _run(_lib.KIND_FULL, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
+                ep_damping, ep_itts, None, False, nargout, debug_cov)
+
+
+def gf_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
+                                    ep_fraction, ep_damping, ep_itts, constraints, w_fixed, tune_hypers,
+                                    nargout=6, debug_cov=False):
+    """matlab/gf_ep_modulator_nmf_constraints.m: box-constrained parameters, balanced model."""
+    return _run(_lib.KIND_FULL, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
+                ep_damping, ep_itts, (constraints, w_fixed, tune_hypers), True, nargout, debug_cov)
+
+
+def ihgp_ep_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
+                          ep_fraction, ep_damping, ep_itts, nargout=6):
+    """Power EP with the infinite-horizon (steady-state gain) approximation.
+    Drop-in for matlab/ihgp_ep_modulator_nmf.m."""
+    return _run(_lib.KIND_IHGP, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
+                ep_damping, ep_itts, None, True, nargout, False)
+
+
+def ihgp_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
+                                      ep_fraction, ep_damping, ep_itts, constraints, w_fixed, tune_hypers,
+                                      nargout=6):
+    """matlab/ihgp_ep_modulator_nmf_constraints.m (its nlZ mode carries the site
+    vectors from step to step, :568-615)."""
+    return _run(_lib.KIND_IHGP, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
+                ep_damping, ep_itts, (constraints, w_fixed, tune_hypers), True, nargout, False,
+                nlz_mode=_lib.MODE_NLZ_RUNNING)
