@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the EP-in-Kalman hot path (BASELINE.json metric: EP filter+smoother
+time-steps/sec, FP64).
+
+Workload (BASELINE.json configs[1], "C2"): ihgp_ep_modulator_nmf, predict mode,
+D = 16 subbands (exp kernel) x N = 3 NMF modulators (matern52), state dim 41,
+likModulatorPreCalcwn with the 9th-order symmetric rule (77 sigma points), link
+softplus(g-1), alpha = 0.75, ep_itts = 20, damping linspace(0.01, 0.1, 20),
+T = 100 000 synthetic "speech-shaped" samples, one signal per GPU.
+
+A bench "step" is one complete EP run over the signal: ep_itts filter+smoother
+sweeps.  time-steps/sec = T * ep_itts * steps / time  (sweeps =
+ep_itts in predict mode).  Host-side setup the reference also does once per call
+with MATLAB built-ins (ss, balance, lti_disc, 1216 DAREs) is outside the timed
+region and reported as setup_s.
+
+  value : device-timed, model/tables/signal already resident in HBM
+  e2e   : the same run through the C ABI call nsagp_ep_ihgp with HOST buffers
+          (H2D of signal+model+tables, D2H of Eft/Varft/lb/ub inside the timed region)
+  --impl reference : the oracle restatement of the reference's MATLAB loop on the
+          host cores (the reference itself cannot run: no MATLAB/Octave), one
+          independent clip per core, bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "nonstationary-audio-gp_b200"
+
+D, N, T_FULL = 16, 3, 100000
+K1, K2 = "exp", "matern52"
+ALPHA, SHIFT, P_CUB = 0.75, 1.0, 9
+EP_ITTS = 20
+WORKLOAD = ("C2: ihgp_ep_modulator_nmf predict mode, D=16 exp subbands x N=3 matern52 modulators (n=41), "
+            "likModulatorPreCalcwn p=9 (S=77), alpha=0.75, ep_itts=20, T=100000, 1 signal per GPU")
+
+
+def damping(itts):
+    return np.linspace(0.01, 0.1, itts)
+
+
+def make_signal(nsagp, seed, T):
+    rng = np.random.default_rng(seed)
+    hyp = nsagp.synth.speech_hypers(D, N, rng)
+    y, _, _ = nsagp.synth.sample_signal(hyp, K1, K2, T, rng, link_shift=SHIFT, sqrt_model=True)
+    return hyp, y
+
+
+def host_setup(nsagp, hyp):
+    """What the .m wrapper keeps in MATLAB: ss, balance, lti_disc, DARE tables."""
+    F, L, Qc, H, Pinf = nsagp.ss_modulators_nmf(hyp.w_sub(), hyp.w_mod(), K1, K2)[:5]
+    F, L, H, Pinf = nsagp.ssmodel.balance(F, L, H, Pinf)
+    A, Q = nsagp.lti_disc(F, L, Qc, 1.0)
+    Q = (Q + Q.T) / 2
+    mdl = nsagp.to_block_model(A, Q, H, Pinf, D, N)
+    tabs = nsagp.tables.build_tables(mdl, want_smoother=True)
+    return mdl, tabs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------- CPU arms
+def _oracle_clip(args):
+    """One independent clip through the oracle (runs in a worker process)."""
+    seed, T, itts = args
+    nsagp = importlib.import_module(PKG)
+    from oracle import cubature as ocub, ihgp_ep, lik as olik, ssmodel as oss
+    hyp, y = make_signal(nsagp, seed, T)
+    wo, xo = ocub.utp_ws(P_CUB, N)
+    mom = olik.make_mom("precalc", olik.softplus_link(SHIFT), wn=wo, xn_unscaled=xo)
+    ss = lambda x, p1, p2, k1, k2: oss.ss_modulators_nmf(p1, p2, k1, k2)
+    t = np.arange(1.0, T + 1.0)
+    # setup (model + tables) is excluded from the timed loops, as on the GPU side
+    lik_param, param1, param2, Wnmf = oss.unpack_log(hyp.pack_log(), 1, D, N)
+    A, Q, H, Pinf = ihgp_ep._model(lik_param, param1, param2, ss, t, K1, K2)
+    tabs = ihgp_ep.ihgp_setup(A, Q, H)
+    t0 = time.perf_counter()
+    ihgp_ep.ihgp_ep_core(A, tabs["Q"], H, Pinf, lik_param, Wnmf, y, mom, ALPHA, damping(itts), itts,
+                         np.arange(T), tabs=tabs)
+    return time.perf_counter() - t0
+
+
+def cpu_arm(steps, warmup, T_sample, itts, cores):
+    """Oracle port on `cores` host cores, one clip per core per step."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_clip, [(1000 + 17 * it + c, T_sample, itts) for c in range(cores)])
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    per_step = float(np.mean(times))
+    return cores * T_sample * itts / per_step, per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    T_sample, itts = 150, EP_ITTS
+    value, per_step = cpu_arm(args.steps, args.warmup, T_sample, itts, cores)
+    sample = "%d independent clips (one per core) of T=%d, ep_itts=%d per step; NumPy oracle port" % (cores, T_sample, itts)
+    line = {"impl": "reference", "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value,
+            "unit": "time-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "reference = MATLAB; MATLAB/Octave absent, so the oracle "
+                       "restatement of matlab/ihgp_ep_modulator_nmf.m is timed on the host cores"},
+            "cpu_baseline": {"value": value, "unit": "time-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "time-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import ctypes as C
+
+    import torch
+    nsagp = importlib.import_module(PKG)
+    lib_mod = nsagp._lib
+    L = lib_mod.lib()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    lib_mod.check(L.nsagp_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    lib_mod.check(L.nsagp_set_stream(C.c_void_p(stream.cuda_stream)))
+
+    T, itts = args.T, args.ep_itts
+    t0 = time.perf_counter()
+    hyp, y = make_signal(nsagp, 2026 + rank, T)            # one independent clip per rank (weak scaling)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mdl, tabs = host_setup(nsagp, hyp)
+    setup_s = time.perf_counter() - t0
+    wn, xn = nsagp.utp_ws(P_CUB, N)
+    mom = nsagp.likModulatorPreCalcwn(nsagp.Softplus(SHIFT), wn, xn)
+    lik_param = np.log([hyp.w_lik])
+    damp = damping(itts)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------
+    plan = nsagp.Plan(lib_mod.KIND_IHGP, [mdl], [(mom, lik_param, hyp.W)], ALPHA, damp, itts, y[None, :],
+                      lib_mod.MODE_PREDICT, tables=[tabs])
+    for _ in range(args.warmup):
+        plan.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    L.nsagp_launch_count(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    phase = {"adf": 0.0, "fixed_filter": 0.0, "smoother": 0.0, "site_update": 0.0, "total": 0.0}
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                       # evict the previous run's arrays from L2
+        ev[i][0].record(stream)
+        plan.run()
+        ev[i][1].record(stream)
+        tm = plan.timings()
+        for k in phase:
+            phase[k] += tm[k]
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = int(L.nsagp_launch_count(0))
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    chk = plan.fetch(0, ("nlZ", "n_negcav"))
+    plan.close()
+
+    # ---- end-to-end arm: C ABI call with host buffers ------------------------
+    Tm = (T, D + N)
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    y_pin = pin((T,)); y_pin[:] = y
+    outs = {k: pin(Tm) for k in ("Eft", "Varft", "lb", "ub")}
+    keep = []
+    cm = lib_mod.Model()
+    arrs = [lib_mod.as_f64(a) for a in (mdl.A, mdl.Q, mdl.Pinf, mdl.h)]
+    cm.D, cm.N, cm.bz, cm.bg = mdl.D, mdl.N, mdl.bz, mdl.bg
+    cm.A, cm.Q, cm.Pinf, cm.h = [lib_mod.dptr(a) for a in arrs]
+    cl = mom.c_lik(lik_param, hyp.W, keep)
+    pp, pg = tabs.packed()
+    r = lib_mod.as_f64(tabs.r); pp = lib_mod.as_f64(pp); pg = lib_mod.as_f64(pg)
+    ct = lib_mod.Tables(r.size, lib_mod.dptr(r), lib_mod.dptr(pp), lib_mod.dptr(pg))
+    dmp = lib_mod.as_f64(damp)
+    ep = lib_mod.Ep(ALPHA, lib_mod.dptr(dmp), itts)
+    co = lib_mod.Outputs()
+    for k, a in outs.items():
+        setattr(co, k, lib_mod.dptr(a))
+    h2d = y_pin.nbytes + sum(a.nbytes for a in arrs) + r.nbytes + pp.nbytes + pg.nbytes + hyp.W.nbytes + wn.nbytes + xn.nbytes
+    d2h = sum(a.nbytes for a in outs.values())
+
+    def e2e_call():
+        lib_mod.check(L.nsagp_ep_ihgp(C.byref(cm), C.byref(cl), C.byref(ep), C.byref(ct), lib_mod.dptr(y_pin), T,
+                                      lib_mod.MODE_PREDICT, C.byref(co)))
+    for _ in range(min(args.warmup, 2)):
+        e2e_call()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_call()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+
+    # ---- reductions over ranks (max time) ------------------------------------
+    vals = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s, wall = [float(v) for v in vals.cpu()]
+    units = world * T * itts * args.steps
+    value = units / (dev_ms * 1e-3)
+    e2e_value = units / e2e_s
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        n, M = mdl.n, mdl.M
+        # dominant kernel: the sequential ADF filter pass (ihgp_adf_kernel), one launch per run.
+        # algorithmic bytes per step of that pass: read y (8) + write ttau,tnu,R (24M) + write MS (8n) + write lZ (8)
+        adf_bytes = T * (8 + 24 * M + 8 * n + 8)
+        adf_ms = phase["adf"] / args.steps
+        ach = adf_bytes / (adf_ms * 1e-3) / 1e9 if adf_ms > 0 else 0.0
+        # whole-run figure with SURVEY 8d's per-step-per-sweep bytes (8 + 24n + 88M)
+        sweep_bytes = (8 + 24 * n + 88 * M) * T * itts
+        line = {
+            "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value, "unit": "time-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if (T == T_FULL and itts == EP_ITTS) else
+                       "C2 shape with T=%d ep_itts=%d (non-default)" % (T, itts),
+                       "T": T, "ep_itts": itts, "signals_per_gpu": 1, "l2": "flushed between timed runs (256 MiB write)",
+                       "step": "one full EP run = ep_itts filter+smoother sweeps"},
+            "e2e": {"value": e2e_value, "unit": "time-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "call": "nsagp_ep_ihgp (C ABI, host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "ihgp_adf_kernel (sequential ADF filter pass, 1 warp per signal)",
+                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "latency-bound nonlinear recurrence: one step cannot start before the previous ends",
+                         "whole_run_GBps": sweep_bytes / (dev_ms / args.steps * 1e-3) / 1e9},
+            "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+            "adf_only_steps_per_s": T / (adf_ms * 1e-3) if adf_ms > 0 else None,
+            "setup_s": {"host_model_and_dare_tables": setup_s, "signal_generation": gen_s},
+            "check": {"nlZ_first": float(chk["nlZ"][0]), "nlZ_last": float(chk["nlZ"][-1]), "n_negcav": chk["n_negcav"]},
+            "wall_s": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = 1
+            Tc, ic = 400, 6
+            v, per = cpu_arm(1, 0, Tc, ic, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "time-steps/s", "cores": cores, "kind": "port",
+                                    "sample": "NumPy oracle of matlab/ihgp_ep_modulator_nmf.m, same model, T=%d ep_itts=%d (%.1f s)" % (Tc, ic, per)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--T", type=int, default=T_FULL)
+    ap.add_argument("--ep-itts", dest="ep_itts", type=int, default=EP_ITTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,9 @@ typedef struct nsagp_plan nsagp_plan;
 int nsagp_plan_create(nsagp_plan** plan, int32_t kind, int32_t B, const nsagp_model* models,
                       const nsagp_lik* liks, const nsagp_ep* ep, const nsagp_tables* tables,
                       const double* y, int64_t T, int32_t mode);
+/* Full-state predict mode only: also keep the filtered covariances of the last
+ * pass (out.PF, gf_ep_modulator_nmf.m:197) -- doubles the covariance storage. */
+int nsagp_plan_keep_pf(nsagp_plan* plan, int keep);
 int nsagp_plan_run(nsagp_plan* plan);
 int nsagp_plan_fetch(nsagp_plan* plan, int32_t b, nsagp_outputs* out);
 int nsagp_plan_destroy(nsagp_plan* plan);

@@ -106,6 +106,7 @@ def lib():
     L.nsagp_plan_fetch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Outputs)]
     L.nsagp_plan_destroy.argtypes = [C.c_void_p]
     L.nsagp_plan_timings.argtypes = [C.c_void_p, c_double_p, C.c_int32]
+    L.nsagp_plan_keep_pf.argtypes = [C.c_void_p, C.c_int]
     _lib = L
     return L
 
@@ -113,7 +114,7 @@ def lib():
 EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_stream", "nsagp_device_count",
            "nsagp_launch_count", "nsagp_mom_batch", "nsagp_mom_batch_warp", "nsagp_ep_ihgp", "nsagp_ep_full",
            "nsagp_ep_ihgp_batch", "nsagp_ep_full_batch", "nsagp_plan_create", "nsagp_plan_run",
-           "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings"]
+           "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings", "nsagp_plan_keep_pf"]
 
 
 def check(status):

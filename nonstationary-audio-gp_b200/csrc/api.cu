@@ -11,8 +11,8 @@
 #include <vector>
 
 #include "common.cuh"
-#include "gfep.cuh"
 #include "ihgp.cuh"
+#include "gfep.cuh"
 #include "mombatch.cuh"
 
 using namespace nsagp;
@@ -435,7 +435,7 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
         (rc = pl->arena.alloc(&dmc, (size_t)M * BM)) || (rc = pl->arena.upload(&dvm0, vm0)) ||
         (rc = pl->arena.alloc(&dmax, 2)) || (rc = pl->arena.alloc(&dneg, 1)) || (rc = pl->arena.alloc(&dstat, 1)))
       return cleanup(rc);
-    if (kind == 1) {
+    if (kind == 1 && (predict || pl->ep_itts > 1)) {     // the smoother needs the filtered covariances
       if ((rc = pl->arena.alloc(&dV, T * M)) || (rc = pl->arena.alloc(&dPS, (size_t)T * pl->PB))) return cleanup(rc);
     }
     St.y = dy; St.ttau = dtt; St.tnu = dtn; St.R = dR; St.MS = dMS; St.E = dE; St.V = dV; St.lZ = dlZ; St.PS = dPS;
@@ -452,13 +452,20 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
       (rc = pl->arena.alloc(&pl->d_nlZ, (size_t)B * (pl->ep_itts + 1))) ||
       (rc = pl->arena.alloc(&pl->d_diag, (size_t)B * pl->ep_itts * 2)))
     return cleanup(rc);
-  if (predict) {
-    if ((rc = pl->arena.alloc(&pl->d_MF, (size_t)B * T * pl->n))) return cleanup(rc);
-    if (kind == 1 && (rc = pl->arena.alloc(&pl->d_PF, (size_t)B * T * pl->PB))) return cleanup(rc);
-  }
+  if (predict && (rc = pl->arena.alloc(&pl->d_MF, (size_t)B * T * pl->n))) return cleanup(rc);
   cudaEventCreate(&pl->ev[0]);
   cudaEventCreate(&pl->ev[1]);
   *out_plan = pl;
+  return NSAGP_OK;
+}
+
+int nsagp_plan_keep_pf(nsagp_plan* pl, int keep) {
+  if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
+  if (keep && !pl->d_PF) {
+    if (pl->kind != 1 || pl->mode != NSAGP_MODE_PREDICT)
+      return fail(NSAGP_ERR_INVALID, "filtered covariances exist only in the full-state predict mode");
+    return pl->arena.alloc(&pl->d_PF, (size_t)pl->B * pl->T * pl->PB);
+  }
   return NSAGP_OK;
 }
 
@@ -580,9 +587,9 @@ int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ) {
   const size_t sm = (size_t)4 * pl->M * TPB * sizeof(double) + lik_smem_bytes(pl);
   const dim3 grid((unsigned)((pl->T - 1 + TPB - 1) / TPB), pl->B);
   DISPATCH_DP(pl->DP, {
-    auto kern = ihgp_site_update_kernel<DP_, TPB>;
+    auto kern = site_update_kernel<DP_, TPB, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, pl->alpha, damp, write_lZ);
+    kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, pl->alpha, damp, write_lZ, 0);
   });
   LAUNCH_CHECK();
   return NSAGP_OK;
@@ -772,7 +779,9 @@ static int run_hostbuf(int kind, int32_t B, const nsagp_model* models, const nsa
   nsagp_plan* pl = nullptr;
   int rc = nsagp_plan_create(&pl, kind, B, models, liks, ep, tables, y, T, mode);
   if (rc) return rc;
-  rc = nsagp_plan_run(pl);
+  for (int b = 0; b < B && !rc; ++b)
+    if (outs[b].PF) rc = nsagp_plan_keep_pf(pl, 1);
+  if (!rc) rc = nsagp_plan_run(pl);
   for (int b = 0; b < B && !rc; ++b) rc = nsagp_plan_fetch(pl, b, &outs[b]);
   nsagp_plan_destroy(pl);
   return rc;

@@ -1,3 +1,504 @@
-// Full-state Power-EP kernels (gf_ep_modulator_nmf) -- see gfep.cuh body below.
+// Full-state Power-EP kernels (gf_ep_modulator_nmf).
+//
+// Reference recursion: matlab/gf_ep_modulator_nmf.m:126-184 (filter), :207-274
+// (RTS smoother + site update), :384-522 (nlZ mode).  The reference's n-by-n
+// covariance is block diagonal with one b-by-b block per latent and stays so
+// under its own update, hence the state here is M independent
+// (m_b, P_b) pairs coupled only through the moment matching.
+//   * filter passes run sequentially, one warp per signal, lanes over blocks
+//     (and over sigma points inside mom_warp);
+//   * the RTS smoother is linear once the filtered estimates exist: a chunked
+//     three-phase scan over (E, g, L) elements (Sarkka & Garcia-Fernandez 2021),
+//     where phase 3 re-applies the reference's literal step inside each chunk;
+//   * the smoother-side site update is independent per time step (siteupdate.cuh).
 #pragma once
 #include "common.cuh"
+#include "mom.cuh"
+
+namespace nsagp {
+
+// C = A * B (b-by-b, column-major, padded to BM)
+template <int BM>
+__device__ __forceinline__ void mat_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < BM; ++j)
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < BM; ++l) s = fma(A[i + l * BM], B[l + j * BM], s);
+      C[i + j * BM] = s;
+    }
+}
+
+// C = A * B' + Q
+template <int BM>
+__device__ __forceinline__ void mat_mul_bt_add(const double* A, const double* B, const double* Q, double* C) {
+#pragma unroll
+  for (int j = 0; j < BM; ++j)
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < BM; ++l) s = fma(A[i + l * BM], B[j + l * BM], s);
+      C[i + j * BM] = s + Q[i + j * BM];
+    }
+}
+
+// ---------------------------------------------------------------- filter pass
+// One warp per signal, steps 0..T-1.  mom_all: moment matching at every observed
+// step (first EP iteration) or only at k == T-1.  nlz: nlZ-mode update rules
+// (clamp at every step, all-sites z-form when any site is at the bound, :424-439).
+template <int DP, int BM>
+__global__ void __launch_bounds__(32)
+gfep_filter_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
+                   int mom_all, double ep_damp, int nlz, int store) {
+  const DevProblem& P_ = probs[blockIdx.x];
+  const DevState& St = states[blockIdx.x];
+  const int lane = threadIdx.x;
+  const int M = P_.M;
+  const bool active = lane < M;
+  const int n = active ? lane : M - 1;
+
+  extern __shared__ double sm[];
+  double* s_mu = sm;
+  double* s_s2 = sm + 32;
+  double* s_W = sm + 64;
+  double* s_wn = s_W + DP * kNP;
+  double* s_xn = s_wn + P_.S;
+  for (int i = lane; i < DP * kNP; i += 32) s_W[i] = P_.W[i];
+  for (int i = lane; i < P_.S; i += 32) s_wn[i] = P_.wn[i];
+  for (int i = lane; i < kNP * P_.S; i += 32) s_xn[i] = P_.xn[i];
+  __syncwarp();
+  MomParams mp;
+  mp.D = P_.D; mp.N = P_.N; mp.S = P_.S; mp.kind = P_.lik_kind; mp.sn2 = P_.sn2; mp.shift = P_.link_shift;
+  mp.W = s_W; mp.wn = s_wn; mp.xn = s_xn;
+
+  double A[BM * BM], Q[BM * BM], hv[BM], m[BM], P[BM * BM];
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) {
+    A[i] = P_.A[n * BM * BM + i];
+    Q[i] = P_.Q[n * BM * BM + i];
+    P[i] = P_.Pinf[n * BM * BM + i];                  // :117
+  }
+#pragma unroll
+  for (int i = 0; i < BM; ++i) { hv[i] = P_.h[n * BM + i]; m[i] = 0.0; }   // :116
+  const int off = P_.off[n];
+  const int b = P_.off[n + 1] - off;
+
+  for (long long k = 0; k < T; ++k) {
+    if (k > 0) {                                       // :129-132
+      double t[BM], AP[BM * BM];
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < BM; ++j) s = fma(A[i + j * BM], m[j], s);
+        t[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < BM; ++i) m[i] = t[i];
+      mat_mul<BM>(A, P, AP);
+      mat_mul_bt_add<BM>(AP, A, Q, P);
+    }
+    const double y = St.y[k];
+    if (!isnan(y)) {                                   // :135
+      double fmu = 0.0, HPH = 0.0, Wv[BM], hP[BM];
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        fmu = fma(hv[i], m[i], fmu);
+        double w = 0.0, g = 0.0;
+#pragma unroll
+        for (int j = 0; j < BM; ++j) {
+          w = fma(P[i + j * BM], hv[j], w);            // W = P*H'
+          g = fma(hv[j], P[j + i * BM], g);            // H*P
+        }
+        Wv[i] = w; hP[i] = g;
+      }
+#pragma unroll
+      for (int i = 0; i < BM; ++i) HPH = fma(hP[i], hv[i], HPH);   // diag(H*P*H')
+      if (nlz && active && !(HPH > 0.0)) atomicCAS(St.status, 0, 2);   // `keyboard` trap (:408-410)
+
+      double tt = St.ttau[k * M + n], tn = St.tnu[k * M + n];
+      if (mom_all || k == T - 1) {                     // :141
+        if (active) { s_mu[lane] = fmu; s_s2[lane] = HPH; }
+        __syncwarp();
+        double d1, d2;
+        const double lz = mom_warp<DP>(mp, 1.0, y, s_mu, s_s2, lane, d1, d2);   // alpha = 1 (:144)
+        __syncwarp();
+        const double den = 1.0 + d2 * HPH;
+        tt = (1.0 - ep_damp) * tt + ep_damp * (-d2 / den);                      // :147
+        tn = (1.0 - ep_damp) * tn + ep_damp * ((d1 - fmu * d2) / den);          // :148
+        if (!nlz) tt = fmax(tt, 0.0);                                           // :151
+        if (lane == 0) St.lZ[k] = lz;
+        if (active && !nlz) St.R[k * M + n] = 1.0 / tt;                         // :154
+      }
+      if (nlz) tt = fmax(tt, 0.0);                                              // :425
+      if (active) { St.ttau[k * M + n] = tt; St.tnu[k * M + n] = tn; }
+
+      const bool at_bound = (tt == 0.0);
+      const bool zform = nlz ? (__any_sync(0xffffffffu, active && at_bound) != 0) : at_bound;
+      if (zform) {                                      // :162-169 / :428-433
+        const double z = tt * HPH + 1.0;
+        const double gk = tt / z;
+        const double v = (tt * fmu - tn) / z;
+#pragma unroll
+        for (int i = 0; i < BM; ++i) m[i] = fma(-Wv[i], v, m[i]);
+#pragma unroll
+        for (int j = 0; j < BM; ++j)
+#pragma unroll
+          for (int i = 0; i < BM; ++i) P[i + j * BM] = fma(-(Wv[i] * gk), Wv[j], P[i + j * BM]);
+      } else {                                          // :171-176 / :435-438
+        const double g = 1.0 / (HPH + 1.0 / tt);
+        const double v = tn / tt - fmu;
+#pragma unroll
+        for (int i = 0; i < BM; ++i) m[i] = fma(Wv[i] * g, v, m[i]);
+#pragma unroll
+        for (int j = 0; j < BM; ++j)
+#pragma unroll
+          for (int i = 0; i < BM; ++i) P[i + j * BM] = fma(-(Wv[i] * g), hP[j], P[i + j * BM]);   // P - K*H*P
+      }
+    }
+    if (active && store) {                              // :181-182
+#pragma unroll
+      for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P_.n + off + i] = m[i];
+      double* dst = St.PS + ((size_t)k * M + n) * BM * BM;
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) dst[i] = P[i];
+      if (k == T - 1) {
+        double e = 0.0, v = 0.0;
+#pragma unroll
+        for (int i = 0; i < BM; ++i) {
+          e = fma(hv[i], m[i], e);
+          double g = 0.0;
+#pragma unroll
+          for (int j = 0; j < BM; ++j) g = fma(hv[j], P[j + i * BM], g);
+          v = fma(g, hv[i], v);
+        }
+        St.E[k * M + n] = e;
+        St.V[k * M + n] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------- RTS smoother
+template <int BM>
+struct RtsMap {            // x_k = E x_{k+1} + g ;  P_k = E P_{k+1} E' + L
+  double E[BM * BM], g[BM], L[BM * BM];
+};
+
+// Per-(block, step) smoother quantities from the filtered estimate
+// (gf_ep_modulator_nmf.m:210-226): PSkp = A PSk A' + Q, G = PSk A' / PSkp.
+template <int BM>
+struct RtsStep {
+  double G[BM * BM], PSkp[BM * BM], PSk[BM * BM], ms[BM], Ams[BM];
+  bool ok;
+};
+
+template <int BM>
+struct RtsElem {
+  const DevProblem& P; const DevState& St; int n, off, b;
+  double A[BM * BM], Q[BM * BM], hv[BM];
+  __device__ RtsElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_) {
+    off = P.off[n]; b = P.off[n + 1] - off;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) { A[i] = P.A[n * BM * BM + i]; Q[i] = P.Q[n * BM * BM + i]; }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BM + i];
+  }
+  __device__ __forceinline__ void step(long long k, RtsStep<BM>& s) const {
+    const double* src = St.PS + ((size_t)k * P.M + n) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) s.PSk[i] = src[i];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
+    double AP[BM * BM];
+    mat_mul<BM>(A, s.PSk, AP);
+    mat_mul_bt_add<BM>(AP, A, Q, s.PSkp);               // :213
+    // Cholesky PSkp = L L' (lower), padding rows/cols treated as identity (:216)
+    double L[BM * BM];
+    s.ok = true;
+#pragma unroll
+    for (int j = 0; j < BM; ++j) {
+      double d = (j < b) ? s.PSkp[j + j * BM] : 1.0;
+#pragma unroll
+      for (int l = 0; l < BM; ++l) if (l < j) d = fma(-L[j + l * BM], L[j + l * BM], d);
+      if (!(d > 0.0)) { s.ok = false; d = 1.0; }
+      const double ljj = sqrt(d);
+      const double inv = 1.0 / ljj;
+      L[j + j * BM] = ljj;
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        if (i > j) {
+          double v = (i < b && j < b) ? s.PSkp[i + j * BM] : 0.0;
+#pragma unroll
+          for (int l = 0; l < BM; ++l) if (l < j) v = fma(-L[i + l * BM], L[j + l * BM], v);
+          L[i + j * BM] = v * inv;
+        } else if (i < j) {
+          L[i + j * BM] = 0.0;
+        }
+      }
+    }
+    // G = PSk*A'/L'/L  (:226): row-wise triangular solves
+    double Bm[BM * BM];
+#pragma unroll
+    for (int j = 0; j < BM; ++j)
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int l = 0; l < BM; ++l) v = fma(s.PSk[i + l * BM], A[j + l * BM], v);   // PSk*A'
+        Bm[i + j * BM] = v;
+      }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double x[BM];
+#pragma unroll
+      for (int j = 0; j < BM; ++j) {                    // x L' = B_i  (forward)
+        double v = Bm[i + j * BM];
+#pragma unroll
+        for (int l = 0; l < BM; ++l) if (l < j) v = fma(-x[l], L[j + l * BM], v);
+        x[j] = v / L[j + j * BM];
+      }
+#pragma unroll
+      for (int jj = 0; jj < BM; ++jj) {                 // g L = x  (backward)
+        const int j = BM - 1 - jj;
+        double v = x[j];
+#pragma unroll
+        for (int l = 0; l < BM; ++l) if (l > j) v = fma(-s.G[i + l * BM], L[l + j * BM], v);
+        s.G[i + j * BM] = v / L[j + j * BM];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < BM; ++j) v = fma(A[i + j * BM], s.ms[j], v);
+      s.Ams[i] = v;
+    }
+  }
+  // the step as an associative element: E = G, g = ms - G A ms, L = PSk - G PSkp G'
+  __device__ __forceinline__ void as_map(const RtsStep<BM>& s, RtsMap<BM>& e) const {
+    double T1[BM * BM];
+    mat_mul<BM>(s.G, s.PSkp, T1);
+#pragma unroll
+    for (int j = 0; j < BM; ++j)
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int l = 0; l < BM; ++l) v = fma(T1[i + l * BM], s.G[j + l * BM], v);
+        e.L[i + j * BM] = s.PSk[i + j * BM] - v;
+        e.E[i + j * BM] = s.G[i + j * BM];
+      }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < BM; ++j) v = fma(s.G[i + j * BM], s.Ams[j], v);
+      e.g[i] = s.ms[i] - v;
+    }
+  }
+  // the reference's literal update (:229-230): m = MSk + G (m - A MSk); P = PSk + G (P - PSkp) G'
+  __device__ __forceinline__ void apply_step(const RtsStep<BM>& s, double (&m)[BM], double (&Pm)[BM * BM]) const {
+    double dm[BM], Dp[BM * BM], T1[BM * BM];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) dm[i] = m[i] - s.Ams[i];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double v = s.ms[i];
+#pragma unroll
+      for (int j = 0; j < BM; ++j) v = fma(s.G[i + j * BM], dm[j], v);
+      m[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) Dp[i] = Pm[i] - s.PSkp[i];
+    mat_mul<BM>(s.G, Dp, T1);
+#pragma unroll
+    for (int j = 0; j < BM; ++j)
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double v = s.PSk[i + j * BM];
+#pragma unroll
+        for (int l = 0; l < BM; ++l) v = fma(T1[i + l * BM], s.G[j + l * BM], v);
+        Pm[i + j * BM] = v;
+      }
+  }
+};
+
+template <int BM>
+__device__ __forceinline__ void rts_compose(RtsMap<BM>& acc, const RtsMap<BM>& e) {
+  // acc <- e o acc
+  double E[BM * BM], T1[BM * BM], g[BM];
+  mat_mul<BM>(e.E, acc.E, E);
+  mat_mul<BM>(e.E, acc.L, T1);
+#pragma unroll
+  for (int i = 0; i < BM; ++i) {
+    double v = e.g[i];
+#pragma unroll
+    for (int j = 0; j < BM; ++j) v = fma(e.E[i + j * BM], acc.g[j], v);
+    g[i] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < BM; ++j)
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double v = e.L[i + j * BM];
+#pragma unroll
+      for (int l = 0; l < BM; ++l) v = fma(T1[i + l * BM], e.E[j + l * BM], v);
+      acc.L[i + j * BM] = v;
+    }
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) acc.E[i] = E[i];
+#pragma unroll
+  for (int i = 0; i < BM; ++i) acc.g[i] = g[i];
+}
+
+template <int BM>
+__device__ __forceinline__ void rts_apply_map(const RtsMap<BM>& e, double (&m)[BM], double (&Pm)[BM * BM]) {
+  double r[BM], T1[BM * BM];
+#pragma unroll
+  for (int i = 0; i < BM; ++i) {
+    double v = e.g[i];
+#pragma unroll
+    for (int j = 0; j < BM; ++j) v = fma(e.E[i + j * BM], m[j], v);
+    r[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < BM; ++i) m[i] = r[i];
+  mat_mul<BM>(e.E, Pm, T1);
+#pragma unroll
+  for (int j = 0; j < BM; ++j)
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double v = e.L[i + j * BM];
+#pragma unroll
+      for (int l = 0; l < BM; ++l) v = fma(T1[i + l * BM], e.E[j + l * BM], v);
+      Pm[i + j * BM] = v;
+    }
+}
+
+// Processing order s = 0..nsteps-1 maps to time k = T-2-s.
+// Phase 1: compose the chunk's maps.  grid (ceil(nchunks/CH), B), block (32, CH).
+template <int BM>
+__global__ void rts_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                                  long long T, double* __restrict__ chunk_buf) {
+  const DevProblem& P = probs[blockIdx.y];
+  const DevState& St = states[blockIdx.y];
+  const int n = threadIdx.x;
+  const long long nsteps = T - 1;
+  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
+  const long long c = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (n >= P.M || c >= nchunks) return;
+  RtsElem<BM> el(P, St, n);
+  RtsStep<BM> st;
+  RtsMap<BM> acc, e;
+  const long long s0 = c * kScanChunk;
+  const long long s1 = (s0 + kScanChunk < nsteps) ? s0 + kScanChunk : nsteps;
+  bool ok = true;
+  el.step(T - 2 - s0, st); ok = ok && st.ok;
+  el.as_map(st, acc);
+  for (long long s = s0 + 1; s < s1; ++s) {
+    el.step(T - 2 - s, st); ok = ok && st.ok;
+    el.as_map(st, e);
+    rts_compose<BM>(acc, e);
+  }
+  if (!ok) atomicCAS(St.status, 0, 1);
+  constexpr int W = 2 * BM * BM + BM;
+  double* dst = chunk_buf + (((size_t)blockIdx.y * nchunks + c) * P.M + n) * W;
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) { dst[i] = acc.E[i]; dst[BM * BM + BM + i] = acc.L[i]; }
+#pragma unroll
+  for (int i = 0; i < BM; ++i) dst[BM * BM + i] = acc.g[i];
+}
+
+// Phase 2: carry (m, P) across chunks from the filtered estimate at T-1.
+template <int BM>
+__global__ void __launch_bounds__(32)
+rts_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
+                 const double* __restrict__ chunk_buf, double* __restrict__ start_buf) {
+  const DevProblem& P = probs[blockIdx.x];
+  const DevState& St = states[blockIdx.x];
+  const int n = threadIdx.x;
+  if (n >= P.M) return;
+  const long long nsteps = T - 1;
+  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
+  const int off = P.off[n], b = P.off[n + 1] - off;
+  double m[BM], Pm[BM * BM];
+#pragma unroll
+  for (int i = 0; i < BM; ++i) m[i] = (i < b) ? St.MS[(T - 1) * P.n + off + i] : 0.0;
+  const double* src0 = St.PS + ((size_t)(T - 1) * P.M + n) * BM * BM;
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) Pm[i] = src0[i];
+  constexpr int W = 2 * BM * BM + BM;
+  constexpr int SW = BM * BM + BM;
+  for (long long c = 0; c < nchunks; ++c) {
+    const size_t base = (((size_t)blockIdx.x * nchunks + c) * P.M + n);
+    double* st = start_buf + base * SW;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) st[i] = m[i];
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) st[BM + i] = Pm[i];
+    const double* src = chunk_buf + base * W;
+    RtsMap<BM> e;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) { e.E[i] = src[i]; e.L[i] = src[BM * BM + BM + i]; }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) e.g[i] = src[BM * BM + i];
+    rts_apply_map<BM>(e, m, Pm);
+  }
+}
+
+// Phase 3: the reference's literal smoother step inside each chunk; overwrite the
+// stored estimates, emit marginals and convergence diagnostics (:229-234,271-272).
+template <int BM>
+__global__ void rts_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                                 long long T, const double* __restrict__ start_buf) {
+  const DevProblem& P = probs[blockIdx.y];
+  const DevState& St = states[blockIdx.y];
+  const int n = threadIdx.x;
+  const long long nsteps = T - 1;
+  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
+  const long long c = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (n >= P.M || c >= nchunks) return;
+  RtsElem<BM> el(P, St, n);
+  RtsStep<BM> st;
+  constexpr int SW = BM * BM + BM;
+  const double* s0p = start_buf + (((size_t)blockIdx.y * nchunks + c) * P.M + n) * SW;
+  double m[BM], Pm[BM * BM];
+#pragma unroll
+  for (int i = 0; i < BM; ++i) m[i] = s0p[i];
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) Pm[i] = s0p[BM + i];
+  const long long s0 = c * kScanChunk;
+  const long long s1 = (s0 + kScanChunk < nsteps) ? s0 + kScanChunk : nsteps;
+  double mdM = 0.0, mdP = 0.0;
+  for (long long s = s0; s < s1; ++s) {
+    const long long k = T - 2 - s;
+    el.step(k, st);
+    el.apply_step(st, m, Pm);
+#pragma unroll
+    for (int i = 0; i < BM; ++i) if (i < el.b) St.MS[k * P.n + el.off + i] = m[i];
+    double* dst = St.PS + ((size_t)k * P.M + n) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) dst[i] = Pm[i];
+    double e = 0.0, v = 0.0;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      e = fma(el.hv[i], m[i], e);
+      double g = 0.0;
+#pragma unroll
+      for (int j = 0; j < BM; ++j) g = fma(el.hv[j], Pm[j + i * BM], g);
+      v = fma(g, el.hv[i], v);
+    }
+    mdM = fmax(mdM, fabs(St.E[k * P.M + n] - e));
+    mdP = fmax(mdP, fabs(St.V[k * P.M + n] - v));
+    St.E[k * P.M + n] = e;
+    St.V[k * P.M + n] = v;
+  }
+  atomic_max_nonneg(St.maxdiff, mdM);
+  atomic_max_nonneg(St.maxdiff + 1, mdP);
+}
+
+}  // namespace nsagp

@@ -384,11 +384,16 @@ __global__ void affine_apply_kernel(const DevProblem* __restrict__ probs, const 
 // -------------------------------------------------------- site update (EP)
 // One thread per time step k in [0, T-1): cavity from the smoothed marginal,
 // moments, damped Power-EP update on sites with positive cavity variance
-// (:397-436).  grid = (ceil((T-1)/TPB), B).
-template <int DP, int TPB>
+// (ihgp_ep_modulator_nmf.m:397-436; gf_ep_modulator_nmf.m:236-267, :486-510).
+// FULL = false: marginal variance from the steady-state table (IHGP);
+// FULL = true : marginal variance from the smoothed covariance (St.V).
+// clamp_R: the full-state predict mode clamps ttau at 0 and refreshes R for every
+// site after the update (:262-265); its nlZ mode and IHGP do not.
+// grid = (ceil((T-1)/TPB), B).
+template <int DP, int TPB, bool FULL>
 __global__ void __launch_bounds__(TPB)
-ihgp_site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                        long long T, double alpha, double ep_damp, int write_lZ) {
+site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                   long long T, double alpha, double ep_damp, int write_lZ, int clamp_R) {
   const DevProblem& P = probs[blockIdx.y];
   const DevState& St = states[blockIdx.y];
   const int tid = threadIdx.x;
@@ -409,37 +414,50 @@ ihgp_site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __
   __syncthreads();
   if (k >= T - 1) return;
   const double y = St.y[k];
-  if (isnan(y)) {                          // :398
-    if (write_lZ) St.lZ[k] = 0.0;
+  if (isnan(y)) {                          // ihgp :398, gf_ep :237
+    if (!FULL && write_lZ) St.lZ[k] = 0.0; // IHGP accumulates a scalar: no term for this step
     return;
   }
   const MomParams mp = make_mom_params(P, s_W, s_wn, s_xn);
   for (int n = 0; n < M; ++n) {
-    const int idx = lookup_smoother(P.r, P.thr, nr, St.R[k * M + n]);
-    const double vm = P.vmtab[(size_t)n * nr + idx];
+    double vm;
+    if (FULL) {
+      vm = St.V[k * M + n];
+    } else {
+      const int idx = lookup_smoother(P.r, P.thr, nr, St.R[k * M + n]);
+      vm = P.vmtab[(size_t)n * nr + idx];
+    }
     const double mm = St.E[k * M + n];
-    const double vcav = 1.0 / (1.0 / vm - alpha * St.ttau[k * M + n]);      // :407
-    const double mcav = vcav * (mm / vm - alpha * St.tnu[k * M + n]);       // :408
+    const double vcav = 1.0 / (1.0 / vm - alpha * St.ttau[k * M + n]);      // ihgp :407
+    const double mcav = vcav * (mm / vm - alpha * St.tnu[k * M + n]);       // ihgp :408
     s_mu[n * TPB + tid] = mcav;
     s_s2[n * TPB + tid] = vcav;
   }
   const double lz = mom_thread<DP>(mp, alpha, y, s_mu + tid, s_s2 + tid, TPB, s_d1 + tid, s_d2 + tid);
-  if (write_lZ) St.lZ[k] = lz;             // :420 (only from the second iteration on)
+  if (write_lZ) St.lZ[k] = lz;             // ihgp :420 only from the second iteration on
   int neg = 0;
   const double keep = 1.0 - ep_damp * alpha;
   for (int n = 0; n < M; ++n) {
     const double vcav = s_s2[n * TPB + tid];
-    if (vcav > 0.0) {                      // :411
+    double tt = St.ttau[k * M + n];
+    const bool upd = vcav > 0.0;           // ihgp :411
+    if (upd) {
       const double mcav = s_mu[n * TPB + tid];
       const double d1 = s_d1[n * TPB + tid], d2 = s_d2[n * TPB + tid];
       const double den = 1.0 + d2 * vcav;
-      const double tt = keep * St.ttau[k * M + n] + ep_damp * (-d2 / den);             // :428
-      const double tn = keep * St.tnu[k * M + n] + ep_damp * ((d1 - mcav * d2) / den);  // :430
-      St.ttau[k * M + n] = tt;
+      tt = keep * tt + ep_damp * (-d2 / den);                                            // :428
+      const double tn = keep * St.tnu[k * M + n] + ep_damp * ((d1 - mcav * d2) / den);   // :430
       St.tnu[k * M + n] = tn;
-      St.R[k * M + n] = 1.0 / tt;          // :434 (no clamp in the smoother pass)
     } else {
       ++neg;
+    }
+    if (clamp_R) {
+      tt = fmax(tt, 0.0);                  // gf_ep :262
+      St.ttau[k * M + n] = tt;
+      St.R[k * M + n] = 1.0 / tt;          // gf_ep :265
+    } else if (upd) {
+      St.ttau[k * M + n] = tt;
+      if (!FULL) St.R[k * M + n] = 1.0 / tt;   // ihgp :434 (no clamp in the smoother pass)
     }
   }
   if (neg) atomicAdd(St.negcav, (unsigned long long)neg);

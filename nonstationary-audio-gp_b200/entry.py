@@ -146,6 +146,11 @@ class Plan:
                                        _lib.dptr(y), self.T, mode))
         self._keep = keep
 
+    def keep_pf(self, keep=True):
+        """Also keep the filtered covariances of the last pass (out.PF); full-state predict mode."""
+        _lib.check(_lib.lib().nsagp_plan_keep_pf(self._h, int(keep)))
+        return self
+
     def run(self):
         _lib.check(_lib.lib().nsagp_plan_run(self._h))
         return self
@@ -250,6 +255,8 @@ def _run(kind, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_
     mode = _lib.MODE_PREDICT if predict else nlz_mode
     with Plan(kind, [mdl], [(mom, lik_param, Wnmf)], ep_fraction, ep_damping, ep_itts, yall[None, :], mode,
               tables=tabs) as plan:
+        if predict and debug_cov and kind == _lib.KIND_FULL and nargout > 5:
+            plan.keep_pf()
         plan.run()
         if predict:
             res = _predict_outputs(plan, mdl, return_ind, nargout, debug_cov)
