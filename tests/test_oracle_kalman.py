@@ -1,0 +1,146 @@
+"""CPU: pin the oracle's filter / smoother / EP plumbing with known answers.
+
+With a Gaussian pseudo-likelihood per latent the EP recursion of
+gf_ep_modulator_nmf.m is exact Kalman filtering + RTS smoothing, which must agree
+with a direct dense GP regression built from the same state-space prior."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import gf_ep, ihgp_ep, lik as olik, ssmodel as oss
+
+
+def _model(D=2, N=1, k1="matern32", k2="matern52", seed=0):
+    rng = np.random.default_rng(seed)
+    ws = np.concatenate([rng.uniform(0.5, 1.0, D), rng.uniform(5, 20, D), np.linspace(0.8, 0.2, D)])
+    wm = np.concatenate([rng.uniform(1, 2, N), rng.uniform(10, 30, N)])
+    F, L, Qc, H, Pinf = oss.ss_modulators_nmf(ws, wm, k1, k2)
+    A, Q = oss.lti_disc(F, L, Qc, 1.0)
+    return A, Q, H, Pinf
+
+
+def _gaussian_mom(Ysite, Rsite):
+    """mom closure of independent Gaussian observations y_i ~ N(f_i, R_i) of every latent."""
+    def mom(hyp, mu, s2, W, ep_frac, yall, k):
+        v = s2 + Rsite / ep_frac
+        r = Ysite[:, k] - mu
+        lZ = float(np.sum(-0.5 * np.log(2 * np.pi * v) - 0.5 * r * r / v))
+        return lZ, r / v, -1.0 / v
+    return mom
+
+
+def test_stationarity_of_discretisation():
+    """lti_disc: Pinf is the stationary covariance, A Pinf A' + Q = Pinf."""
+    for k1, k2 in (("exp", "matern52"), ("matern32", "matern52"), ("matern52", "matern72")):
+        A, Q, H, Pinf = _model(k1=k1, k2=k2)
+        assert np.allclose(A @ Pinf @ A.T + Q, Pinf, rtol=1e-9, atol=1e-12)
+
+
+def test_kalman_rts_equals_dense_gp():
+    A, Q, H, Pinf = _model()
+    M, n = H.shape
+    T = 25
+    rng = np.random.default_rng(1)
+    Y = rng.normal(0, 1, (M, T))
+    R = rng.uniform(0.05, 0.5, M)
+    yall = np.zeros(T)                                   # only marks "observed"
+    Eft, Varft, lb, ub, out = gf_ep.gf_ep_core(A, Q, H, Pinf, np.log([1.0]), np.ones((2, 1)), yall,
+                                               _gaussian_mom(Y, R), 1.0, [1.0], 1, True, np.arange(T))
+    # dense GP: cov(f_i(s), f_j(t)) = H A^|s-t| Pinf H'
+    Apow = [np.eye(n)]
+    for _ in range(T):
+        Apow.append(A @ Apow[-1])
+    K = np.zeros((M * T, M * T))
+    for s in range(T):
+        for t in range(T):
+            blk = H @ (Apow[s - t] @ Pinf if s >= t else Pinf @ Apow[t - s].T) @ H.T
+            K[s * M:(s + 1) * M, t * M:(t + 1) * M] = blk
+    Rn = np.tile(R, T)
+    yv = Y.T.reshape(-1)
+    S = K + np.diag(Rn)
+    mean = K @ np.linalg.solve(S, yv)
+    var = np.diag(K - K @ np.linalg.solve(S, K))
+    assert np.allclose(Eft.T.reshape(-1), mean, rtol=1e-8, atol=1e-10)
+    assert np.allclose(Varft.T.reshape(-1), var, rtol=1e-8, atol=1e-10)
+    # log marginal likelihood from the ADF pass = exact Gaussian evidence
+    sign, logdet = np.linalg.slogdet(S)
+    ref = -0.5 * yv @ np.linalg.solve(S, yv) - 0.5 * logdet - 0.5 * M * T * math.log(2 * math.pi)
+    assert abs(-out["nlZ"][0] - ref) < 1e-8 * abs(ref)
+    # sites are exactly the Gaussian observations
+    assert np.allclose(out["ttau"], (1 / R)[:, None]) and np.allclose(out["tnu"], Y / R[:, None])
+
+
+def test_covariance_stays_block_diagonal():
+    """the dense P of the reference never leaves the block structure."""
+    A, Q, H, Pinf = _model(D=3, N=2)
+    T = 40
+    rng = np.random.default_rng(2)
+    W = 0.1 * np.abs((2.0 * rng.random((3, 2))) ** 2 - 0.2)
+    y = rng.normal(0, 0.05, T)
+    mom = olik.make_mom("power", olik.softplus_link(0.0), p=5)
+    Eft, Varft, lb, ub, out = gf_ep.gf_ep_core(A, Q, H, Pinf, np.log([1e-2]), W, y, mom, 0.5, [0.5, 0.5], 2, True,
+                                               np.arange(T), want_cov=True)
+    st = ihgp_ep.block_starts(H)
+    mask = np.ones(A.shape, bool)
+    for i in range(H.shape[0]):
+        mask[st[i]:st[i + 1], st[i]:st[i + 1]] = False
+    assert np.all(out["PS"][mask] == 0.0) and np.all(out["PF"][mask] == 0.0)
+
+
+def test_two_update_branches_agree():
+    """Info-form (tau == 0 branch written for general tau) and gain-form updates of
+    gf_ep_modulator_nmf.m:162-176 are the same map when tau > 0."""
+    A, Q, H, Pinf = _model(D=2, N=2)
+    rng = np.random.default_rng(3)
+    m = rng.normal(size=A.shape[0]); P = Pinf.copy()
+    tt = rng.uniform(0.5, 3, H.shape[0]); tn = rng.normal(size=H.shape[0])
+    fmu = H @ m; W = P @ H.T; HPH = np.diag(H @ P @ H.T)
+    m1, P1 = gf_ep._filter_update_predict(m, P, H, fmu, W, HPH, tt, tn)
+    z = tt * HPH + 1
+    K = W * (tt / z)[None, :]
+    v = tt * fmu - tn
+    m2 = m - W @ (v / z); P2 = P - K @ W.T
+    assert np.allclose(m1, m2, rtol=1e-11, atol=1e-13) and np.allclose(P1, P2, rtol=1e-11, atol=1e-13)
+
+
+def test_merge_inputs_unique_first():
+    yall, ret = gf_ep.merge_inputs([3, 1, 2], [30, 10, 20], [2, 2.5, 1])
+    assert np.array_equal(np.isnan(yall), [False, False, True, False])
+    assert np.array_equal(yall[[0, 1, 3]], [10, 20, 30]) and np.array_equal(ret, [1, 2, 0])
+    yall, ret = gf_ep.merge_inputs([1, 2, 3], [1, 2, 3], [1, 2, 3])
+    assert np.array_equal(yall, [1, 2, 3]) and np.array_equal(ret, [0, 1, 2])
+
+
+def test_ihgp_tables_solve_their_equations():
+    """Forward table rows satisfy the predictive Riccati equation at the coarse
+    nodes; smoother rows satisfy X = G X G' + QQ; interpolation is linear in r."""
+    A, Q, H, Pinf = _model(D=2, N=1, k1="exp")
+    Q = (Q + Q.T) / 2
+    il = ihgp_ep.block_starts(H)
+    r, ro, PPo, PP = ihgp_ep.forward_tables(A, Q, H, il)
+    for n in range(H.shape[0]):
+        ii = slice(il[n], il[n + 1]); b = il[n + 1] - il[n]
+        Ab, Qb, hb = A[ii, ii], Q[ii, ii], H[n, ii]
+        for j in (0, 13, 31):
+            X = PPo[n][j].reshape((b, b), order="F")
+            K = Ab @ X @ hb / (hb @ X @ hb + ro[j])
+            res = Ab @ X @ Ab.T - np.outer(K, hb @ X @ Ab.T) + Qb - X
+            assert np.abs(res).max() < 1e-9 * max(np.abs(X).max(), 1e-12)
+        # fine grid: endpoints coincide with the coarse nodes, interior is a convex combination
+        assert np.allclose(PP[n][0], PPo[n][0]) and np.allclose(PP[n][-1], PPo[n][-1])
+        j = 57
+        lo = np.searchsorted(ro, r[j]) - 1
+        w = (r[j] - ro[lo]) / (ro[lo + 1] - ro[lo])
+        assert np.allclose(PP[n][j], (1 - w) * PPo[n][lo] + w * PPo[n][lo + 1], rtol=1e-12, atol=0)
+
+
+def test_lookup_rules():
+    """Inf -> index 1 in the filter rule; ties -> first index; NaN -> first."""
+    r = np.logspace(-2, 4, 200)
+    assert ihgp_ep._lookup_filter(r, np.inf) == 0
+    assert ihgp_ep._lookup_filter(r, np.nan) == 0
+    assert ihgp_ep._lookup_filter(r, -3.0) == 0
+    assert ihgp_ep._lookup_filter(r, 1e9) == 199
+    assert ihgp_ep._lookup_filter(r, r[17]) == 17
+    assert ihgp_ep._lookup_filter(r, 1e30) == 0          # all |r - R| round to R: tie -> first
