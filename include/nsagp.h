@@ -178,6 +178,11 @@ int nsagp_plan_create(nsagp_plan** plan, int32_t kind, int32_t B, const nsagp_mo
 /* Full-state predict mode only: also keep the filtered covariances of the last
  * pass (out.PF, gf_ep_modulator_nmf.m:197) -- doubles the covariance storage. */
 int nsagp_plan_keep_pf(nsagp_plan* plan, int keep);
+/* Form of the sequential (ADF) filter pass, the only part of the schedule that is a
+ * nonlinear recurrence in time (ihgp_ep_modulator_nmf.m:253-271, gf_ep_modulator_nmf.m:141-156):
+ * 0 = one CTA per problem (default; lowest latency per step, for few long signals),
+ * 1 = one warp per problem (for batches of many more problems than SMs). */
+int nsagp_plan_set_adf_form(nsagp_plan* plan, int form);
 int nsagp_plan_run(nsagp_plan* plan);
 int nsagp_plan_fetch(nsagp_plan* plan, int32_t b, nsagp_outputs* out);
 int nsagp_plan_destroy(nsagp_plan* plan);

@@ -14,7 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libnsagp.so")
-_SOURCES = ["api.cu", "api_full.inc", "common.cuh", "mom.cuh", "mombatch.cuh", "lookup.cuh", "ihgp.cuh", "gfep.cuh"]
+_SOURCES = ["api.cu", "api_full.inc", "common.cuh", "mom.cuh", "momcta.cuh", "mombatch.cuh", "lookup.cuh", "ihgp.cuh",
+            "gfep.cuh", "adfcta.cuh"]
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -107,6 +108,7 @@ def lib():
     L.nsagp_plan_destroy.argtypes = [C.c_void_p]
     L.nsagp_plan_timings.argtypes = [C.c_void_p, c_double_p, C.c_int32]
     L.nsagp_plan_keep_pf.argtypes = [C.c_void_p, C.c_int]
+    L.nsagp_plan_set_adf_form.argtypes = [C.c_void_p, C.c_int]
     _lib = L
     return L
 
@@ -114,7 +116,8 @@ def lib():
 EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_stream", "nsagp_device_count",
            "nsagp_launch_count", "nsagp_mom_batch", "nsagp_mom_batch_warp", "nsagp_ep_ihgp", "nsagp_ep_full",
            "nsagp_ep_ihgp_batch", "nsagp_ep_full_batch", "nsagp_plan_create", "nsagp_plan_run",
-           "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings", "nsagp_plan_keep_pf"]
+           "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings", "nsagp_plan_keep_pf",
+           "nsagp_plan_set_adf_form"]
 
 
 def check(status):

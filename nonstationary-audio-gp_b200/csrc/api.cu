@@ -14,6 +14,7 @@
 #include "ihgp.cuh"
 #include "gfep.cuh"
 #include "mombatch.cuh"
+#include "adfcta.cuh"
 
 using namespace nsagp;
 
@@ -129,6 +130,7 @@ struct nsagp_plan {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> phase_ev;
   double timings[5] = {0, 0, 0, 0, 0};
+  int adf_form = 0;             // 0: one CTA per signal (latency), 1: one warp per signal (many signals)
   bool ran = false;
 };
 
@@ -469,6 +471,13 @@ int nsagp_plan_keep_pf(nsagp_plan* pl, int keep) {
   return NSAGP_OK;
 }
 
+int nsagp_plan_set_adf_form(nsagp_plan* pl, int form) {
+  if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
+  if (form != 0 && form != 1) return fail(NSAGP_ERR_INVALID, "adf form must be 0 (CTA per signal) or 1 (warp per signal)");
+  pl->adf_form = form;
+  return NSAGP_OK;
+}
+
 int nsagp_plan_destroy(nsagp_plan* pl) {
   if (!pl) return NSAGP_OK;
   pl->arena.release();
@@ -552,13 +561,51 @@ int save_diag(nsagp_plan* pl, int itt) {
   return NSAGP_OK;
 }
 
+// Launch geometry of the CTA-cooperative sequential passes (adfcta.cuh).
+struct AdfGeom {
+  int threads, dpt;
+  bool single;
+  size_t smem;
+  bool tab_smem;
+};
+
+AdfGeom adf_geom(const nsagp_plan* pl, bool want_tables) {
+  AdfGeom g;
+  const int want = ((4 * pl->S + 31) / 32) * 32;
+  g.threads = std::min(want, kAdfMaxThreads);
+  g.single = 4 * pl->S <= g.threads;
+  g.dpt = (pl->D <= 16) ? 4 : 8;
+  const int NV = 2 * g.dpt + 3;
+  const AdfSmem with(g.threads / 32, NV, pl->S, pl->M, pl->nr, pl->BM, true);
+  const AdfSmem without(g.threads / 32, NV, pl->S, pl->M, pl->nr, pl->BM, false);
+  g.tab_smem = want_tables && (size_t)with.total * 8 <= 200 * 1024;
+  g.smem = (size_t)(g.tab_smem ? with.total : without.total) * 8;
+  return g;
+}
+
+#define DISPATCH_DPT(DPTV, ...)                                           \
+  if ((DPTV) == 4) { constexpr int DPT_ = 4; __VA_ARGS__; } else { constexpr int DPT_ = 8; __VA_ARGS__; }
+#define DISPATCH_SINGLE(SV, ...)                                          \
+  if (SV) { constexpr bool SINGLE_ = true; __VA_ARGS__; } else { constexpr bool SINGLE_ = false; __VA_ARGS__; }
+
 int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double damp, int running) {
-  const size_t sm = 64 * sizeof(double) + lik_smem_bytes(pl);
-  DISPATCH_DP(pl->DP, DISPATCH_BM(pl->BM, {
-    auto kern = ihgp_adf_kernel<DP_, BM_>;
-    if (sm > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<pl->B, 32, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
-  }));
+  if (pl->adf_form == 1) {
+    const size_t sm = 64 * sizeof(double) + lik_smem_bytes(pl);
+    DISPATCH_DP(pl->DP, DISPATCH_BM(pl->BM, {
+      auto kern = ihgp_adf_kernel<DP_, BM_>;
+      if (sm > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      kern<<<pl->B, 32, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
+    }));
+    LAUNCH_CHECK();
+    return NSAGP_OK;
+  }
+  const AdfGeom g = adf_geom(pl, k1 - k0 > 64);      // the table copy only pays off on a long pass
+  DISPATCH_DPT(g.dpt, DISPATCH_BM(pl->BM, DISPATCH_SINGLE(g.single, {
+    auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_>;
+    if (g.smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    kern<<<pl->B, g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running,
+                                                 g.tab_smem ? 1 : 0);
+  })));
   LAUNCH_CHECK();
   return NSAGP_OK;
 }

@@ -151,6 +151,11 @@ class Plan:
         _lib.check(_lib.lib().nsagp_plan_keep_pf(self._h, int(keep)))
         return self
 
+    def set_adf_form(self, form):
+        """0: one CTA per problem (default), 1: one warp per problem (large batches)."""
+        _lib.check(_lib.lib().nsagp_plan_set_adf_form(self._h, int(form)))
+        return self
+
     def run(self):
         _lib.check(_lib.lib().nsagp_plan_run(self._h))
         return self
