@@ -142,6 +142,11 @@ int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_f
                          int64_t T, const double* y, const double* mu, const double* s2,
                          double* lZ, double* dlZ, double* d2lZ);
 
+/* Test hook: the straight-line FP64 routines used on the critical path of the
+ * sequential passes (csrc/fastmath.cuh), evaluated for n host values.
+ * op: 0 1/x, 1 1/sqrt(x), 2 sqrt(x), 3 exp(x), 4 log(x) for x >= 1, 5 log(1+exp(x)). */
+int nsagp_fastmath_eval(int32_t op, int64_t n, const double* x, double* out);
+
 /* ihgp_ep_modulator_nmf / ihgp_ep_modulator_nmf_constraints
  * (ihgp_ep_modulator_nmf.m:195-526 predict, :533-624 nlZ).  y[T] is `yall` after
  * the merge/sort of train and test inputs (:58-67). */

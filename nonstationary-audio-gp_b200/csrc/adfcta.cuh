@@ -4,13 +4,20 @@
 // matlab/gf_ep_modulator_nmf.m:126-184 / :400-447 (full-state filter).
 //
 // The pass is a nonlinear recurrence in time, so one step's latency is the whole
-// cost.  The CTA splits a step as
-//   warp 0, lane n < M : Kalman predict / update of block n (registers);
-//   all 4*S threads    : the sigma-point moment matching (momcta.cuh);
-// with three CTA barriers per step.  Everything a step touches that does not
-// depend on the recurrence (y, old site values) is loaded one step ahead; the
-// steady-state tables and the look-up thresholds sit in shared memory, and the
-// nearest-neighbour look-up first tries the previous step's row.
+// cost.  Roles inside the CTA (momcta.cuh):
+//   warp 0 ("Kalman warp"), lane n < M : predict / update of latent block n, in registers;
+//   warps 1.. ("moment warps")         : the sigma-point moment matching, 4 threads per point.
+// Per step the Kalman warp publishes the cavity (predicted marginal) in shared
+// memory and arrives at a named barrier; the moment warps wait there, integrate,
+// leave their partial sums in shared memory and arrive at a second barrier the
+// Kalman warp waits on.  While the moment warps work, the Kalman warp issues the
+// previous step's global stores and its logarithm / division for the outputs that
+// are not part of the recurrence (lZ, R).  On the critical path the site update and
+// the Kalman gain are fused into two reciprocals (momcta.cuh: adf_site_from_sums,
+// and the "z-form" of the update, gf_ep_modulator_nmf.m:162-169, which equals the
+// gain form :171-176 algebraically), the steady-state tables sit in shared memory
+// and are indexed by a threshold search on ttau itself (no division), trying the
+// previous step's row first.
 #pragma once
 #include "common.cuh"
 #include "lookup.cuh"
@@ -21,88 +28,124 @@
 
 namespace nsagp {
 
-constexpr int kAdfMaxThreads = 384;
+constexpr int kAdfMaxMomThreads = 352;     // 11 moment warps + the Kalman warp = 384 threads
 
-// ind = #{i : thr[i] <= R}, trying `hint` first (R moves slowly from step to step).
-__device__ __forceinline__ int nearest_by_threshold_hint(const double* thr, int nr, double R, int hint) {
-  if (hint >= 0 && hint < nr) {
-    const double lo = (hint > 0) ? thr[hint - 1] : -INFINITY;
-    const double hi = (hint < nr - 1) ? thr[hint] : INFINITY;
-    if (lo <= R && !(hi <= R)) return hint;
+// idx = #{i : thr[i] <= 1/tt} = #{i : tt <= cthr[i]} (cthr descending, nr-1 entries; host-built so
+// that the decision is bit-identical to the reference's min(abs(r-R)) with R = 1./ttau).
+// R moves by a few grid cells per step, so ten thresholds around the previous row are loaded at
+// once and counted; the binary search only runs when the answer lies outside that window.
+__device__ __forceinline__ int lookup_by_ttau(const double* cthr, int nr, double tt, int hint) {
+  const int last = nr - 2;
+  const int h = min(max(hint, 0), nr - 1);
+  const int lo = max(h - 5, 0), hi = min(h + 4, last);
+  int cnt = 0;
+  bool first = false, end = false;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const int i = min(lo + j, hi);
+    const bool le = tt <= cthr[i];
+    cnt += (lo + j <= hi && le) ? 1 : 0;
+    if (j == 0) first = le;
+    end = le;                               // after the loop: the comparison at hi
   }
-  return nearest_by_threshold(thr, nr, R);
+  if ((lo == 0 || first) && (hi == last || !end)) return lo + cnt;
+  int a = 0, b = nr - 1;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    if (tt <= cthr[mid]) a = mid + 1; else b = mid;
+  }
+  return a;
 }
 
-__device__ __forceinline__ int lookup_filter_hint(const double* r, const double* thr, int nr, double R, int hint) {
-  if (!(R > 0.0)) return 0;
-  if (isinf(R)) return 0;
-  if (R >= kLookupBig) return nearest_bruteforce(r, nr, R);
-  return nearest_by_threshold_hint(thr, nr, R, hint);
-}
-
-// Shared-memory layout helper (doubles).
+// Shared-memory layout (doubles) of the CTA kernels.
 struct AdfSmem {
-  int mu, s2, part, fin, wn, xn, thr, hph, wtab, total;
-  __host__ __device__ AdfSmem(int nwarps, int NV, int S, int M, int nr, int BM, bool tables) {
+  int mom, wn, xn, q, cthr, hph, wtab, sdt, rs2t, total;
+  __host__ __device__ AdfSmem(int nmw, int NVP, int S, int M, int N, int nr, int BM, bool tables, bool fullstate) {
     int o = 0;
-    mu = o; o += 32;
-    s2 = o; o += 32;
-    part = o; o += nwarps * 4 * NV;
-    fin = o; o += 4 * NV;
+    mom = o; o += 72 + nmw * 4 * NVP;
     wn = o; o += S;
     xn = o; o += kNP * S;
-    thr = o; o += tables ? (nr > 0 ? nr - 1 : 0) : 0;
+    q = o; o += fullstate ? M * BM * BM : 0;
+    cthr = o; o += tables ? nr - 1 : 0;
     hph = o; o += tables ? M * (nr + 1) : 0;
     wtab = o; o += tables ? M * (nr + 1) * BM : 0;
+    sdt = o; o += tables ? N * (nr + 1) : 0;
+    rs2t = o; o += tables ? N * (nr + 1) : 0;
     total = o;
   }
 };
 
+// Loop of a moment thread: steps k0..k1-1, moments wherever the Kalman warp asks.
+template <int DPT, bool SINGLE>
+__device__ __forceinline__ void adf_moment_loop(const MomParams& mp, const double* __restrict__ yv, long long T,
+                                                long long k0, long long k1, int mom_all, bool skip_nan,
+                                                double* s_mom, int mtid, int nmt, int nthreads) {
+  MomCtaThread<DPT> th;
+  th.init(mp, mtid);
+  const double noise = mp.sn2;                        // alpha = 1 in the filter (:256 / :144)
+  double* s_part = s_mom + MomCta<DPT>::kCav;
+  double y_nx = yv[k0];
+  for (long long k = k0; k < k1; ++k) {
+    const double y = y_nx;
+    const bool do_mom = (mom_all || k == T - 1) && !(skip_nan && isnan(y));
+    if (do_mom) {
+      named_bar_sync(kBarCavity, nthreads);
+      mom_cta_points<DPT, SINGLE>(mp, th, noise, y, s_mom, s_part, mtid, nmt);
+      named_bar_arrive(kBarSums, nthreads);
+    }
+    if (k + 1 < k1) y_nx = yv[k + 1];      // lands while the Kalman warp works
+  }
+}
+
 // ----------------------------------------------------------------- IHGP
 // Steps k0..k1-1.  mom_all: moment matching at every step (first pass) or only at
 // k == T-1.  running: the _constraints nlZ variant's running site vectors.
-// tab_smem: tables copied to shared memory (host checked that they fit).
-template <int DPT, int BM, bool SINGLE>
-__global__ void __launch_bounds__(kAdfMaxThreads)
+// TABS: steady-state tables in shared memory (the host checks that they fit).
+template <int DPT, int BM, bool SINGLE, bool TABS>
+__global__ void __launch_bounds__(32 + kAdfMaxMomThreads)
 ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                    long long T, long long k0, long long k1, int mom_all, double ep_damp, int running,
-                    int tab_smem) {
-  constexpr int NV = MomCta<DPT>::NV;
+                    long long T, long long k0, long long k1, int mom_all, double ep_damp, int running) {
+  constexpr int NVP = MomCta<DPT>::NVP;
   const DevProblem& P = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nthreads = blockDim.x;
-  const int M = P.M, nr = P.nr;
-  const bool kal = tid < 32;                 // warp 0 owns the Kalman blocks
-  const bool active = kal && lane < M;
-  const int n = (lane < M) ? lane : M - 1;
+  const int nthreads = blockDim.x, nmt = nthreads - 32, nmw = nmt >> 5;
+  const int M = P.M, nr = P.nr, D = P.D;
 
   extern __shared__ double sm[];
-  const AdfSmem L(nthreads >> 5, NV, P.S, M, nr, BM, tab_smem != 0);
-  double* s_mu = sm + L.mu;
-  double* s_s2 = sm + L.s2;
-  double* s_part = sm + L.part;
-  double* s_fin = sm + L.fin;
+  const AdfSmem L(nmw, NVP, P.S, M, P.N, nr, BM, TABS, false);
+  double* s_mom = sm + L.mom;
   double* s_wn = sm + L.wn;
   double* s_xn = sm + L.xn;
   for (int i = tid; i < P.S; i += nthreads) s_wn[i] = P.wn[i];
   for (int i = tid; i < kNP * P.S; i += nthreads) s_xn[i] = P.xn[i];
-  const double* thr = P.thr;
-  const double* hphtab = P.HPHtab;
-  const double* wtab = P.Wtab;
-  if (tab_smem) {
-    double* d0 = sm + L.thr; double* d1_ = sm + L.hph; double* d2_ = sm + L.wtab;
-    for (int i = tid; i < nr - 1; i += nthreads) d0[i] = P.thr[i];
-    for (int i = tid; i < M * (nr + 1); i += nthreads) d1_[i] = P.HPHtab[i];
-    for (int i = tid; i < M * (nr + 1) * BM; i += nthreads) d2_[i] = P.Wtab[i];
-    thr = d0; hphtab = d1_; wtab = d2_;
+  // steady-state tables: shared memory when they fit (TABS), else straight from HBM/L2
+  const double* cthr = TABS ? sm + L.cthr : P.cthr;
+  const double* hphtab = TABS ? sm + L.hph : P.HPHtab;
+  const double* wtab = TABS ? sm + L.wtab : P.Wtab;
+  const double* sdtab = TABS ? sm + L.sdt : P.SDtab;
+  const double* rs2tab = TABS ? sm + L.rs2t : P.RS2tab;
+  if (TABS) {
+    for (int i = tid; i < nr - 1; i += nthreads) sm[L.cthr + i] = P.cthr[i];
+    for (int i = tid; i < M * (nr + 1); i += nthreads) sm[L.hph + i] = P.HPHtab[i];
+    for (int i = tid; i < M * (nr + 1) * BM; i += nthreads) sm[L.wtab + i] = P.Wtab[i];
+    for (int i = tid; i < P.N * (nr + 1); i += nthreads) { sm[L.sdt + i] = P.SDtab[i]; sm[L.rs2t + i] = P.RS2tab[i]; }
   }
   __syncthreads();
-  MomParams mp = make_mom_params(P, P.W, s_wn, s_xn);
-  MomCtaThread<DPT> th;
-  th.init(mp, tid);
-  const double pep = pep_const(mp.kind, mp.sn2, 1.0);     // alpha = 1 in the filter (:256)
+  const MomParams mp = make_mom_params(P, P.W, s_wn, s_xn);
 
+  if (tid >= 32) {
+    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, k1, mom_all, true, s_mom, tid - 32, nmt, nthreads);
+    return;
+  }
+
+  // ------------------------------------------------------------ Kalman warp
+  const bool active = lane < M;
+  const int n = active ? lane : M - 1;
+  const bool is_mod = active && n >= D;
+  const double pep = pep_const(mp.kind, mp.sn2, 1.0);     // alpha = 1 in the filter (:256)
+  MomCtaSumAddr<DPT> sum_addr;
+  sum_addr.init(s_mom + MomCta<DPT>::kCav, n, D);
   double A[BM * BM], hA[BM], hv[BM], m[BM];
 #pragma unroll
   for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
@@ -123,86 +166,125 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     const double Rp = (ttp == 0.0) ? INFINITY : St.R[(k0 - 1) * M + n];
     idx = lookup_filter(P.r, P.thr, nr, Rp);
   }
-  double tt_run = 0.0, tn_run = 0.0;
-  // one-step-ahead loads of everything that does not depend on the recurrence
+  // one-step-ahead loads of what does not depend on the recurrence
   double y_nx = St.y[k0];
-  double tt_nx = kal ? St.ttau[k0 * M + n] : 0.0;
-  double tn_nx = kal ? St.tnu[k0 * M + n] : 0.0;
-  double R_nx = (kal && !mom_all) ? St.R[k0 * M + n] : 0.0;
+  double tt_nx = St.ttau[k0 * M + n];
+  double tn_nx = St.tnu[k0 * M + n];
+  double R_nx = mom_all ? 0.0 : St.R[k0 * M + n];
+  // outputs of the previous step, stored while the moment warps work
+  bool pend = false, pend_mom = false;
+  long long pk = 0;
+  double p_tt = 0.0, p_tn = 0.0, p_ttraw = 0.0, p_R = 0.0, p_Z = 1.0;
 
   for (long long k = k0; k < k1; ++k) {
-    const double y = y_nx;
     const double tt_ld = tt_nx, tn_ld = tn_nx, R_ld = R_nx;
-    if (k + 1 < k1) {
-      y_nx = St.y[k + 1];
-      if (kal) {
-        tt_nx = St.ttau[(k + 1) * M + n];
-        tn_nx = St.tnu[(k + 1) * M + n];
-        if (!mom_all) R_nx = St.R[(k + 1) * M + n];
-      }
-    }
     const bool do_mom = mom_all || k == T - 1;
+    // A missing sample (y = NaN) is not skipped by the reference (:253-271 has no isnan test):
+    // its moments are NaN, so ttau = max(NaN, 0) = 0, tnu = NaN and lZ = log(pEP * jitter).
+    // The moment warps never see it; the same values are produced here.
+    const bool y_nan = isnan(y_nx);
+    const bool ask = do_mom && !y_nan;
     double Am[BM], Wv[BM];
-    double fmu = 0.0, HPH = 0.0;
-    if (kal) {
+    double fmu = 0.0;
 #pragma unroll
-      for (int i = 0; i < BM; ++i) {
-        double acc = 0.0;
+    for (int i = 0; i < BM; ++i) {
+      double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < BM; ++j) acc = fma(A[i + j * BM], m[j], acc);
-        Am[i] = acc;
-        fmu = fma(hA[i], m[i], fmu);          // fmu = (H*A)*m (:250)
-      }
-      const double* wrow = wtab + ((size_t)n * (nr + 1) + idx) * BM;
-      HPH = hphtab[(size_t)n * (nr + 1) + idx];
-#pragma unroll
-      for (int i = 0; i < BM; ++i) Wv[i] = wrow[i];
-      if (do_mom && active) { s_mu[lane] = fmu; s_s2[lane] = HPH; }
+      for (int j = 0; j < BM; ++j) acc = fma(A[i + j * BM], m[j], acc);
+      Am[i] = acc;
+      fmu = fma(hA[i], m[i], fmu);            // fmu = (H*A)*m (:250)
     }
-    if (do_mom) {
-      __syncthreads();
-      mom_cta<DPT, SINGLE>(mp, th, 1.0, y, s_mu, s_s2, s_part, s_fin);
-    }
-    if (kal) {
-      double tt, tn, Rk;
-      if (do_mom) {
-        double Z, d1, d2;
-        mom_cta_result<DPT>(mp, pep, s_fin, n, Z, d1, d2);
-        const double tt_old = running ? tt_run : tt_ld;
-        const double tn_old = running ? tn_run : tn_ld;
-        const double den = 1.0 + d2 * HPH;
-        tt = (1.0 - ep_damp) * tt_old + ep_damp * (-d2 / den);                  // :265
-        tn = (1.0 - ep_damp) * tn_old + ep_damp * ((d1 - fmu * d2) / den);      // :266
-        Rk = 1.0 / tt;                                                          // :269 (before the clamp)
-        if (lane == 0) St.lZ[k] = log(Z);
-      } else {
-        tt = tt_ld; tn = tn_ld; Rk = R_ld;
-      }
-      tt = fmax(tt, 0.0);                     // NaN -> 0, as MATLAB max (:274)
-      if (tt == 0.0) {
-        Rk = INFINITY;                        // :287
-#pragma unroll
-        for (int i = 0; i < BM; ++i) m[i] = Am[i];
-      } else {
-        const double ys = tn / tt;            // :277
-        const double g = 1.0 / (HPH + Rk);
-        const double innov = ys - fmu;
-#pragma unroll
-        for (int i = 0; i < BM; ++i) m[i] = fma(Wv[i] * g, innov, Am[i]);       // (A-K h A) m + K ys
-      }
-      idx = lookup_filter_hint(P.r, thr, nr, Rk, idx);
+    const double HPH = hphtab[(size_t)n * (nr + 1) + idx];
+    if (ask) {
       if (active) {
-        St.ttau[k * M + n] = tt; St.tnu[k * M + n] = tn; St.R[k * M + n] = Rk;
-#pragma unroll
-        for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P.n + off + i] = m[i];
-        if (k == T - 1) {
-          double e = 0.0;
-#pragma unroll
-          for (int i = 0; i < BM; ++i) e = fma(hv[i], m[i], e);
-          St.E[k * M + n] = e;
+        s_mom[lane] = fmu; s_mom[32 + lane] = HPH;
+        if (is_mod) {
+          s_mom[64 + n - D] = sdtab[(size_t)(n - D) * (nr + 1) + idx];
+          s_mom[68 + n - D] = rs2tab[(size_t)(n - D) * (nr + 1) + idx];
         }
       }
-      tt_run = tt; tn_run = tn;
+      __syncwarp();
+      named_bar_arrive(kBarCavity, nthreads);
+    }
+    {
+      const double* wrow = wtab + ((size_t)n * (nr + 1) + idx) * BM;
+#pragma unroll
+      for (int i = 0; i < BM; ++i) Wv[i] = wrow[i];
+    }
+    // ---- off the critical path: next step's loads, previous step's outputs ----
+    if (k + 1 < k1) {
+      y_nx = St.y[k + 1];
+      tt_nx = St.ttau[(k + 1) * M + n];
+      tn_nx = St.tnu[(k + 1) * M + n];
+      if (!mom_all) R_nx = St.R[(k + 1) * M + n];
+    }
+    if (pend) {
+      double Rk = p_R;
+      if (pend_mom) {
+        Rk = 1.0 / p_ttraw;                                                     // :269 (before the clamp)
+        if (lane == 0) St.lZ[pk] = log(pep * p_Z);
+      }
+      if (p_tt == 0.0) Rk = INFINITY;                                           // :287
+      if (active) {
+        St.ttau[pk * M + n] = p_tt; St.tnu[pk * M + n] = p_tn; St.R[pk * M + n] = Rk;
+#pragma unroll
+        for (int i = 0; i < BM; ++i) if (i < b) St.MS[pk * P.n + off + i] = m[i];
+      }
+    }
+    // ---- this step ----
+    double tt, tn, ttraw, Zm = 1.0;
+    if (do_mom) {
+      double tt_new = NAN, tn_new = NAN;
+      Zm = kJitter;
+      if (ask) {
+        named_bar_sync(kBarSums, nthreads);
+        double Zs, r1, r2;
+        mom_cta_sums<DPT>(sum_addr, nmw, Zs, r1, r2);
+        adf_site_from_sums(Zs, r1, r2, fmu, HPH, tt_new, tn_new, Zm);
+      }
+      const double tt_old = running ? p_tt : tt_ld;
+      const double tn_old = running ? p_tn : tn_ld;
+      ttraw = fma(ep_damp, tt_new, (1.0 - ep_damp) * tt_old);                   // :265
+      tn = fma(ep_damp, tn_new, (1.0 - ep_damp) * tn_old);                      // :266
+    } else {
+      ttraw = tt_ld; tn = tn_ld;
+    }
+    tt = fmax(ttraw, 0.0);                    // NaN -> 0, as MATLAB max (:274)
+    if (tt == 0.0) {
+#pragma unroll
+      for (int i = 0; i < BM; ++i) m[i] = Am[i];                                // :287-289
+      idx = 0;                                // R = Inf: every distance is Inf, min() returns the first index (:239)
+    } else {
+      // (A - K h A) m + K ys with K = W/(HPH + 1/ttau), ys = tnu/ttau  (:291-300), as one reciprocal
+      const double c = (tn - tt * fmu) * rcp_fast(fma(tt, HPH, 1.0));
+#pragma unroll
+      for (int i = 0; i < BM; ++i) m[i] = fma(Wv[i], c, Am[i]);
+      if (do_mom) {
+        idx = (tt > 2e-12) ? lookup_by_ttau(cthr, nr, tt, idx) : lookup_filter(P.r, P.thr, nr, 1.0 / tt);
+      } else {
+        idx = lookup_filter(P.r, P.thr, nr, R_ld);
+      }
+    }
+    pend = true; pend_mom = do_mom; pk = k;
+    p_tt = tt; p_tn = tn; p_ttraw = ttraw; p_R = R_ld; p_Z = Zm;
+  }
+  if (pend) {
+    double Rk = p_R;
+    if (pend_mom) {
+      Rk = 1.0 / p_ttraw;
+      if (lane == 0) St.lZ[pk] = log(pep * p_Z);
+    }
+    if (p_tt == 0.0) Rk = INFINITY;
+    if (active) {
+      St.ttau[pk * M + n] = p_tt; St.tnu[pk * M + n] = p_tn; St.R[pk * M + n] = Rk;
+#pragma unroll
+      for (int i = 0; i < BM; ++i) if (i < b) St.MS[pk * P.n + off + i] = m[i];
+      if (pk == T - 1) {
+        double e = 0.0;
+#pragma unroll
+        for (int i = 0; i < BM; ++i) e = fma(hv[i], m[i], e);
+        St.E[pk * M + n] = e;
+      }
     }
   }
 }
@@ -210,162 +292,178 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
 // ------------------------------------------------------------ full-state EP
 // One CTA per signal, steps 0..T-1 (gf_ep_modulator_nmf.m:126-184; nlZ mode :400-447).
 // mom_all: moment matching at every observed step (first EP iteration) or only at
-// k == T-1.  nlz: nlZ-mode update rules (clamp at every step, all-sites z-form when
-// any site is at the bound, :424-439).
+// k == T-1.  nlz: nlZ-mode rules (clamp at every step, :425).  The measurement
+// update is written in the z-form for every site (:162-169 / :428-433), which is
+// algebraically the gain form (:171-176 / :435-438) and covers ttau = 0 without a branch.
 template <int DPT, int BM, bool SINGLE>
-__global__ void __launch_bounds__(kAdfMaxThreads)
+__global__ void __launch_bounds__(32 + kAdfMaxMomThreads)
 gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
                        int mom_all, double ep_damp, int nlz, int store) {
-  constexpr int NV = MomCta<DPT>::NV;
+  constexpr int NVP = MomCta<DPT>::NVP;
   const DevProblem& P_ = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nthreads = blockDim.x;
-  const int M = P_.M;
-  const bool kal = tid < 32;
-  const bool active = kal && lane < M;
-  const int n = (lane < M) ? lane : M - 1;
+  const int nthreads = blockDim.x, nmt = nthreads - 32, nmw = nmt >> 5;
+  const int M = P_.M, D = P_.D;
 
   extern __shared__ double sm[];
-  const AdfSmem L(nthreads >> 5, NV, P_.S, M, 0, BM, false);
-  double* s_mu = sm + L.mu;
-  double* s_s2 = sm + L.s2;
-  double* s_part = sm + L.part;
-  double* s_fin = sm + L.fin;
+  const AdfSmem L(nmw, NVP, P_.S, M, P_.N, 0, BM, false, true);
+  double* s_mom = sm + L.mom;
   double* s_wn = sm + L.wn;
   double* s_xn = sm + L.xn;
+  double* s_q = sm + L.q;
   for (int i = tid; i < P_.S; i += nthreads) s_wn[i] = P_.wn[i];
   for (int i = tid; i < kNP * P_.S; i += nthreads) s_xn[i] = P_.xn[i];
+  for (int i = tid; i < M * BM * BM; i += nthreads) s_q[i] = P_.Q[i];
   __syncthreads();
-  MomParams mp = make_mom_params(P_, P_.W, s_wn, s_xn);
-  MomCtaThread<DPT> th;
-  th.init(mp, tid);
-  const double pep = pep_const(mp.kind, mp.sn2, 1.0);     // alpha = 1 (:144)
+  const MomParams mp = make_mom_params(P_, P_.W, s_wn, s_xn);
 
-  double A[BM * BM], Q[BM * BM], hv[BM], m[BM], P[BM * BM];
-#pragma unroll
-  for (int i = 0; i < BM * BM; ++i) {
-    A[i] = P_.A[n * BM * BM + i];
-    Q[i] = P_.Q[n * BM * BM + i];
-    P[i] = P_.Pinf[n * BM * BM + i];                  // :117
+  if (tid >= 32) {
+    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, 0, T, mom_all, true, s_mom, tid - 32, nmt, nthreads);
+    return;
   }
+
+  // ------------------------------------------------------------ Kalman warp
+  const bool active = lane < M;
+  const int n = active ? lane : M - 1;
+  const bool is_mod = active && n >= D;
+  const double pep = pep_const(mp.kind, mp.sn2, 1.0);     // alpha = 1 (:144)
+  MomCtaSumAddr<DPT> sum_addr;
+  sum_addr.init(s_mom + MomCta<DPT>::kCav, n, D);
+  const double* Qn = s_q + n * BM * BM;
+  double A[BM * BM], hv[BM], m[BM], P[BM * BM];
 #pragma unroll
-  for (int i = 0; i < BM; ++i) { hv[i] = P_.h[n * BM + i]; m[i] = 0.0; }   // :116
+  for (int i = 0; i < BM * BM; ++i) { A[i] = P_.A[n * BM * BM + i]; P[i] = P_.Pinf[n * BM * BM + i]; }   // :117
+#pragma unroll
+  for (int i = 0; i < BM; ++i) { hv[i] = P_.h[n * BM + i]; m[i] = 0.0; }                                  // :116
   const int off = P_.off[n];
   const int b = P_.off[n + 1] - off;
 
   double y_nx = St.y[0];
-  double tt_nx = kal ? St.ttau[n] : 0.0;
-  double tn_nx = kal ? St.tnu[n] : 0.0;
+  double tt_nx = St.ttau[n];
+  double tn_nx = St.tnu[n];
+  bool pend = false, pend_obs = false, pend_mom = false;
+  long long pk = 0;
+  double p_tt = 0.0, p_tn = 0.0, p_Z = 1.0;
+
+  auto flush = [&](bool last) {
+    // outputs of step pk: (m, P) still hold its posterior (:181-182)
+    if (pend_mom) {
+      if (lane == 0) St.lZ[pk] = log(pep * p_Z);
+      if (active && !nlz) St.R[pk * M + n] = 1.0 / p_tt;                          // :154
+    }
+    if (active && pend_obs) { St.ttau[pk * M + n] = p_tt; St.tnu[pk * M + n] = p_tn; }
+    if (active && store) {
+#pragma unroll
+      for (int i = 0; i < BM; ++i) if (i < b) St.MS[pk * P_.n + off + i] = m[i];
+      double* dst = St.PS + ((size_t)pk * M + n) * BM * BM;
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) dst[i] = P[i];
+      if (last) {
+        double e = 0.0, v = 0.0;
+#pragma unroll
+        for (int i = 0; i < BM; ++i) {
+          e = fma(hv[i], m[i], e);
+          double g = 0.0;
+#pragma unroll
+          for (int j = 0; j < BM; ++j) g = fma(hv[j], P[j + i * BM], g);
+          v = fma(g, hv[i], v);
+        }
+        St.E[pk * M + n] = e;
+        St.V[pk * M + n] = v;
+      }
+    }
+  };
 
   for (long long k = 0; k < T; ++k) {
     const double y = y_nx;
     const double tt_ld = tt_nx, tn_ld = tn_nx;
-    if (k + 1 < T) {
-      y_nx = St.y[k + 1];
-      if (kal) { tt_nx = St.ttau[(k + 1) * M + n]; tn_nx = St.tnu[(k + 1) * M + n]; }
-    }
     const bool obs = !isnan(y);                          // :135 (uniform over the CTA)
     const bool do_mom = obs && (mom_all || k == T - 1);  // :141
+    // predicted moments of step k, kept apart from the posterior of step k-1
+    double mq[BM], Pq[BM * BM];
+    if (k > 0) {                                         // :129-132
+      double AP[BM * BM], Qr[BM * BM];
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) Qr[i] = Qn[i];
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < BM; ++j) s = fma(A[i + j * BM], m[j], s);
+        mq[i] = s;
+      }
+      mat_mul<BM>(A, P, AP);
+      mat_mul_bt_add<BM>(AP, A, Qr, Pq);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BM; ++i) mq[i] = m[i];
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) Pq[i] = P[i];
+    }
     double fmu = 0.0, HPH = 0.0, Wv[BM], hP[BM];
-    if (kal) {
-      if (k > 0) {                                       // :129-132
-        double t[BM], AP[BM * BM];
+    if (obs) {
 #pragma unroll
-        for (int i = 0; i < BM; ++i) {
-          double s = 0.0;
+      for (int i = 0; i < BM; ++i) {
+        fmu = fma(hv[i], mq[i], fmu);
+        double w = 0.0, g = 0.0;
 #pragma unroll
-          for (int j = 0; j < BM; ++j) s = fma(A[i + j * BM], m[j], s);
-          t[i] = s;
+        for (int j = 0; j < BM; ++j) {
+          w = fma(Pq[i + j * BM], hv[j], w);             // W = P*H'
+          g = fma(hv[j], Pq[j + i * BM], g);             // H*P
         }
-#pragma unroll
-        for (int i = 0; i < BM; ++i) m[i] = t[i];
-        mat_mul<BM>(A, P, AP);
-        mat_mul_bt_add<BM>(AP, A, Q, P);
+        Wv[i] = w; hP[i] = g;
       }
-      if (obs) {
 #pragma unroll
-        for (int i = 0; i < BM; ++i) {
-          fmu = fma(hv[i], m[i], fmu);
-          double w = 0.0, g = 0.0;
-#pragma unroll
-          for (int j = 0; j < BM; ++j) {
-            w = fma(P[i + j * BM], hv[j], w);            // W = P*H'
-            g = fma(hv[j], P[j + i * BM], g);            // H*P
-          }
-          Wv[i] = w; hP[i] = g;
+      for (int i = 0; i < BM; ++i) HPH = fma(hP[i], hv[i], HPH);   // diag(H*P*H')
+      if (do_mom) {
+        if (active) {
+          s_mom[lane] = fmu; s_mom[32 + lane] = HPH;
+          if (is_mod) { s_mom[64 + n - D] = sqrt_fast(HPH); s_mom[68 + n - D] = rcp_fast(HPH); }
         }
-#pragma unroll
-        for (int i = 0; i < BM; ++i) HPH = fma(hP[i], hv[i], HPH);   // diag(H*P*H')
-        if (nlz && active && !(HPH > 0.0)) atomicCAS(St.status, 0, 2);   // `keyboard` trap (:408-410)
-        if (do_mom && active) { s_mu[lane] = fmu; s_s2[lane] = HPH; }
+        __syncwarp();
+        named_bar_arrive(kBarCavity, nthreads);
       }
+      if (nlz && active && !(HPH > 0.0)) atomicCAS(St.status, 0, 2);   // `keyboard` trap (:408-410)
     }
-    if (do_mom) {
-      __syncthreads();
-      mom_cta<DPT, SINGLE>(mp, th, 1.0, y, s_mu, s_s2, s_part, s_fin);
+    // ---- off the critical path: next step's loads, previous step's outputs ----
+    if (k + 1 < T) {
+      y_nx = St.y[k + 1];
+      tt_nx = St.ttau[(k + 1) * M + n];
+      tn_nx = St.tnu[(k + 1) * M + n];
     }
-    if (kal) {
-      if (obs) {
-        double tt = tt_ld, tn = tn_ld;
-        if (do_mom) {
-          double Z, d1, d2;
-          mom_cta_result<DPT>(mp, pep, s_fin, n, Z, d1, d2);
-          const double den = 1.0 + d2 * HPH;
-          tt = (1.0 - ep_damp) * tt + ep_damp * (-d2 / den);                      // :147
-          tn = (1.0 - ep_damp) * tn + ep_damp * ((d1 - fmu * d2) / den);          // :148
-          if (!nlz) tt = fmax(tt, 0.0);                                           // :151
-          if (lane == 0) St.lZ[k] = log(Z);
-          if (active && !nlz) St.R[k * M + n] = 1.0 / tt;                         // :154
-        }
-        if (nlz) tt = fmax(tt, 0.0);                                              // :425
-        if (active) { St.ttau[k * M + n] = tt; St.tnu[k * M + n] = tn; }
-
-        const bool at_bound = (tt == 0.0);
-        const bool zform = nlz ? (__any_sync(0xffffffffu, active && at_bound) != 0) : at_bound;
-        if (zform) {                                      // :162-169 / :428-433
-          const double z = tt * HPH + 1.0;
-          const double gk = tt / z;
-          const double v = (tt * fmu - tn) / z;
-#pragma unroll
-          for (int i = 0; i < BM; ++i) m[i] = fma(-Wv[i], v, m[i]);
-#pragma unroll
-          for (int j = 0; j < BM; ++j)
-#pragma unroll
-            for (int i = 0; i < BM; ++i) P[i + j * BM] = fma(-(Wv[i] * gk), Wv[j], P[i + j * BM]);
-        } else {                                          // :171-176 / :435-438
-          const double g = 1.0 / (HPH + 1.0 / tt);
-          const double v = tn / tt - fmu;
-#pragma unroll
-          for (int i = 0; i < BM; ++i) m[i] = fma(Wv[i] * g, v, m[i]);
-#pragma unroll
-          for (int j = 0; j < BM; ++j)
-#pragma unroll
-            for (int i = 0; i < BM; ++i) P[i + j * BM] = fma(-(Wv[i] * g), hP[j], P[i + j * BM]);   // P - K*H*P
-        }
+    if (pend) flush(false);
+    double tt = tt_ld, tn = tn_ld, Zm = 1.0;
+    if (obs) {
+      if (do_mom) {
+        named_bar_sync(kBarSums, nthreads);
+        double Zs, r1, r2, tt_new, tn_new;
+        mom_cta_sums<DPT>(sum_addr, nmw, Zs, r1, r2);
+        adf_site_from_sums(Zs, r1, r2, fmu, HPH, tt_new, tn_new, Zm);
+        tt = fma(ep_damp, tt_new, (1.0 - ep_damp) * tt_ld);                       // :147
+        tn = fma(ep_damp, tn_new, (1.0 - ep_damp) * tn_ld);                       // :148
+        if (!nlz) tt = fmax(tt, 0.0);                                             // :151
       }
-      if (active && store) {                              // :181-182
+      if (nlz) tt = fmax(tt, 0.0);                                                // :425
+      const double rz = rcp_fast(fma(tt, HPH, 1.0));
+      const double c = (tn - tt * fmu) * rz;
+      const double g = tt * rz;
 #pragma unroll
-        for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P_.n + off + i] = m[i];
-        double* dst = St.PS + ((size_t)k * M + n) * BM * BM;
+      for (int i = 0; i < BM; ++i) m[i] = fma(Wv[i], c, mq[i]);
 #pragma unroll
-        for (int i = 0; i < BM * BM; ++i) dst[i] = P[i];
-        if (k == T - 1) {
-          double e = 0.0, v = 0.0;
+      for (int j = 0; j < BM; ++j)
 #pragma unroll
-          for (int i = 0; i < BM; ++i) {
-            e = fma(hv[i], m[i], e);
-            double g = 0.0;
+        for (int i = 0; i < BM; ++i) P[i + j * BM] = fma(-(Wv[i] * g), hP[j], Pq[i + j * BM]);
+    } else {
 #pragma unroll
-            for (int j = 0; j < BM; ++j) g = fma(hv[j], P[j + i * BM], g);
-            v = fma(g, hv[i], v);
-          }
-          St.E[k * M + n] = e;
-          St.V[k * M + n] = v;
-        }
-      }
+      for (int i = 0; i < BM; ++i) m[i] = mq[i];
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) P[i] = Pq[i];
     }
+    pend = true; pend_obs = obs; pend_mom = do_mom; pk = k;
+    p_tt = tt; p_tn = tn; p_Z = Zm;
   }
+  if (pend) flush(true);
 }
 
 }  // namespace nsagp

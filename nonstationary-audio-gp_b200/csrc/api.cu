@@ -78,6 +78,26 @@ double bisect_threshold(const std::vector<double>& r, int i) {
   return x;
 }
 
+// Largest double t > 0 with fl(1/t) >= thr: the nearest-neighbour decision of the reference is
+// taken on R = 1./ttau, and fl(1/t) is non-increasing in t, so comparing ttau with this value
+// is the same decision without the division.
+double bisect_ttau_threshold(double thr) {
+  auto ok = [&](double t) { return 1.0 / t >= thr; };
+  double a = 2.3e-308, b = 1e300;            // ok(a), !ok(b) for any thr in (1e-300, 1e300)
+  uint64_t lo, hi;
+  std::memcpy(&lo, &a, 8);
+  std::memcpy(&hi, &b, 8);
+  while (hi - lo > 1) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    double x;
+    std::memcpy(&x, &mid, 8);
+    if (ok(x)) lo = mid; else hi = mid;
+  }
+  double x;
+  std::memcpy(&x, &lo, 8);
+  return x;
+}
+
 struct DeviceArena {
   std::vector<void*> ptrs;
   size_t bytes = 0;
@@ -268,6 +288,53 @@ int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_f
   return mom_batch_impl(lik, D, N, ep_fraction, T, y, mu, s2, lZ, dlZ, d2lZ, 1);
 }
 
+// ------------------------------------------------------------- fastmath hook
+}  // extern "C"
+
+namespace {
+__global__ void fastmath_kernel(int op, long long n, const double* __restrict__ x, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (op) {
+    case 0: r = rcp_fast(v); break;
+    case 1: r = rsqrt_fast(v); break;
+    case 2: r = sqrt_fast(v); break;
+    case 3: r = exp_fast(v); break;
+    case 4: r = log_ge1_fast(v); break;
+    case 5: r = softplus_fast(v); break;
+    case 6: r = rcp_fast2(v); break;
+    case 7: r = rsqrt_fast2(v); break;
+    default: r = sqrt_fast2(v); break;
+  }
+  out[i] = r;
+}
+}  // namespace
+
+extern "C" {
+
+int nsagp_fastmath_eval(int32_t op, int64_t n, const double* x, double* out) {
+  if (op < 0 || op > 8 || n < 0 || !x || !out) return fail(NSAGP_ERR_INVALID, "bad argument");
+  if (n == 0) return NSAGP_OK;
+  int rc = ensure_stream();
+  if (rc) return rc;
+  DeviceArena ar;
+  double *dx, *dout;
+  if ((rc = ar.alloc(&dx, n)) || (rc = ar.alloc(&dout, n))) { ar.release(); return rc; }
+  auto body = [&]() -> int {
+    CU(cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    fastmath_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(op, n, dx, dout);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return NSAGP_OK;
+  };
+  rc = body();
+  ar.release();
+  return rc;
+}
+
 // ----------------------------------------------------------------------- plan
 int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsagp_model* models,
                       const nsagp_lik* liks, const nsagp_ep* ep, const nsagp_tables* tables, const double* y,
@@ -361,10 +428,11 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
     std::vector<double> vm0(M, 0.0);
     if (kind == 0) {
       const nsagp_tables& tb = tables[b];
-      std::vector<double> r(tb.r, tb.r + nr), thr(nr - 1);
+      std::vector<double> r(tb.r, tb.r + nr), thr(nr - 1), cthr(nr - 1);
       for (int i = 0; i + 1 < nr; ++i) {
         if (!(r[i] > 0.0) || !(r[i + 1] > r[i])) return cleanup(fail(NSAGP_ERR_INVALID, "table grid r must be positive and ascending"));
         thr[i] = bisect_threshold(r, i);
+        cthr[i] = bisect_ttau_threshold(thr[i]);
       }
       std::vector<double> Wtab((size_t)M * (nr + 1) * BM, 0.0), HPH((size_t)M * (nr + 1), 0.0);
       std::vector<double> Gtab, vmtab;
@@ -404,10 +472,19 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
         }
         ppo += (size_t)nr * bs * bs; po += (size_t)bs * bs; ho += bs;
       }
-      double *dr, *dthr, *dWt, *dHPH, *dG = nullptr, *dvm = nullptr;
+      std::vector<double> SDt((size_t)N * (nr + 1)), RS2t((size_t)N * (nr + 1));
+      for (int j = 0; j < N; ++j)
+        for (int row = 0; row <= nr; ++row) {
+          const double v = HPH[(size_t)(D + j) * (nr + 1) + row];
+          SDt[(size_t)j * (nr + 1) + row] = std::sqrt(v);
+          RS2t[(size_t)j * (nr + 1) + row] = 1.0 / v;
+        }
+      double *dr, *dthr, *dcthr, *dWt, *dHPH, *dSD, *dRS2, *dG = nullptr, *dvm = nullptr;
       if ((rc = pl->arena.upload(&dr, r)) || (rc = pl->arena.upload(&dthr, thr)) || (rc = pl->arena.upload(&dWt, Wtab)) ||
-          (rc = pl->arena.upload(&dHPH, HPH)))
+          (rc = pl->arena.upload(&dHPH, HPH)) || (rc = pl->arena.upload(&dcthr, cthr)) ||
+          (rc = pl->arena.upload(&dSD, SDt)) || (rc = pl->arena.upload(&dRS2, RS2t)))
         return cleanup(rc);
+      P.cthr = dcthr; P.SDtab = dSD; P.RS2tab = dRS2;
       if (tb.PG && ((rc = pl->arena.upload(&dG, Gtab)) || (rc = pl->arena.upload(&dvm, vmtab)))) return cleanup(rc);
       P.r = dr; P.thr = dthr; P.Wtab = dWt; P.HPHtab = dHPH; P.Gtab = dG; P.vmtab = dvm;
     } else {
@@ -569,15 +646,16 @@ struct AdfGeom {
   bool tab_smem;
 };
 
-AdfGeom adf_geom(const nsagp_plan* pl, bool want_tables) {
+AdfGeom adf_geom(const nsagp_plan* pl, bool want_tables, bool fullstate) {
   AdfGeom g;
   const int want = ((4 * pl->S + 31) / 32) * 32;
-  g.threads = std::min(want, kAdfMaxThreads);
-  g.single = 4 * pl->S <= g.threads;
+  const int nmt = std::min(want, kAdfMaxMomThreads);      // moment threads
+  g.threads = 32 + nmt;                                   // + the Kalman warp
+  g.single = 4 * pl->S <= nmt;
   g.dpt = (pl->D <= 16) ? 4 : 8;
-  const int NV = 2 * g.dpt + 3;
-  const AdfSmem with(g.threads / 32, NV, pl->S, pl->M, pl->nr, pl->BM, true);
-  const AdfSmem without(g.threads / 32, NV, pl->S, pl->M, pl->nr, pl->BM, false);
+  const int NVP = (2 * g.dpt + 3 + 3) & ~3;
+  const AdfSmem with(nmt / 32, NVP, pl->S, pl->M, pl->N, pl->nr, pl->BM, true, fullstate);
+  const AdfSmem without(nmt / 32, NVP, pl->S, pl->M, pl->N, pl->nr, pl->BM, false, fullstate);
   g.tab_smem = want_tables && (size_t)with.total * 8 <= 200 * 1024;
   g.smem = (size_t)(g.tab_smem ? with.total : without.total) * 8;
   return g;
@@ -599,12 +677,17 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
     LAUNCH_CHECK();
     return NSAGP_OK;
   }
-  const AdfGeom g = adf_geom(pl, k1 - k0 > 64);      // the table copy only pays off on a long pass
+  const AdfGeom g = adf_geom(pl, k1 - k0 > 64, false);      // the table copy only pays off on a long pass
   DISPATCH_DPT(g.dpt, DISPATCH_BM(pl->BM, DISPATCH_SINGLE(g.single, {
-    auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_>;
-    if (g.smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    kern<<<pl->B, g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running,
-                                                 g.tab_smem ? 1 : 0);
+    if (g.tab_smem) {
+      auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_, true>;
+      if (g.smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+      kern<<<pl->B, g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
+    } else {
+      auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_, false>;
+      if (g.smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+      kern<<<pl->B, g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
+    }
   })));
   LAUNCH_CHECK();
   return NSAGP_OK;

@@ -39,6 +39,9 @@ struct DevProblem {
   const double* HPHtab;          // [M][nr+1]      h*PP*h'
   const double* Gtab;            // [M][nr][BM*BM] smoother gain
   const double* vmtab;           // [M][nr]        h*Ps*h'
+  const double* cthr;            // [nr-1] the same thresholds expressed on ttau: 1/ttau >= thr[i]  <=>  ttau <= cthr[i]
+  const double* SDtab;           // [N][nr+1]      sqrt(h*PP*h') of the modulator blocks
+  const double* RS2tab;          // [N][nr+1]      1/(h*PP*h')
 };
 
 // Per-problem mutable state in HBM.  Site arrays are time-major, M contiguous

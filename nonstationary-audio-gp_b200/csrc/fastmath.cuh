@@ -1,0 +1,185 @@
+// Branch-free FP64 elementary functions for the latency-critical sequential passes.
+//
+// The CUDA library versions of 1/x, sqrt, rsqrt, exp and log are correctly handled
+// for every special case, which costs slow-path branches that ptxas will not
+// interleave across independent evaluations.  On the ADF critical path the
+// arguments are known to be ordinary numbers, so these versions start from the
+// hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) and refine with straight-line
+// FMAs.  Accuracy is <= 2 ulp over the stated domains (tests/test_gpu_mom.py checks
+// them against numpy through nsagp_fastmath_eval); the parity budget of the path is
+// 1e-8 relative.
+#pragma once
+#include "common.cuh"
+
+namespace nsagp {
+
+// 1/x for finite normal x (either sign).  Not for 0, Inf, NaN, subnormals.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// 1/sqrt(x) for finite normal x > 0.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * r, r, 0.5);         // (1 - x r^2) / 2
+  r = fma(r, e, r);
+  e = fma(-hx * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-hx * r, r, 0.5);
+  return fma(r, e, r);
+}
+
+// sqrt(x) for x >= 0 finite (returns +0 for 0; NaN for negative x, as sqrt does).
+__device__ __forceinline__ double sqrt_fast(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r;                         // ~ sqrt(x)
+  double h = 0.5 * r;                       // ~ 1 / (2 sqrt(x))
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, x);           // residual
+  g = fma(d, h, g);
+  return (x == 0.0) ? 0.0 : g;              // 0 * Inf = NaN above; negative x stays NaN
+}
+
+// Variants with one Newton step fewer (nsagp_fastmath_eval ops 6-8 measure them).
+__device__ __forceinline__ double rcp_fast2(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_fast2(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-hx * r, r, 0.5);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double sqrt_fast2(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r;
+  double h = 0.5 * r;
+  const double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, x);
+  g = fma(d, h, g);
+  return (x == 0.0) ? 0.0 : g;
+}
+
+// Polynomial coefficients live in constant memory so that they are instruction operands
+// (c[bank][offset]) instead of being re-materialised into registers in every step.
+__constant__ double kExpC[14] = {
+    1.0, 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,
+    1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0};
+__constant__ double kExpK[4] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+                                6755399441055744.0};      // log2(e), -ln2_hi, -ln2_lo, 1.5 * 2^52
+__constant__ double kLogC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                1.479819860511658591e-01,   // fdlibm Lg1..Lg7
+                                6.93147180369123816490e-01, 1.90821492927058770002e-10};   // ln2_hi, ln2_lo
+
+// exp(x), straight-line, for finite x.  The argument is clamped to [-708, 709]: below, the
+// result is exp(-708) = 3.3e-308 instead of a subnormal or 0; above, exp(709) = 8.2e307 instead
+// of Inf.  CHECKED = true additionally returns exactly 0 below -708 and propagates NaN.
+template <bool CHECKED>
+__device__ __forceinline__ double exp_fast_t(double x) {
+  const double xc = fmin(fmax(x, -708.0), 709.0);
+  const double t = fma(xc, kExpK[0], kExpK[3]);      // round-to-nearest-integer trick
+  const int n = __double2loint(t);
+  const double fn = t - kExpK[3];
+  double r = fma(fn, kExpK[1], xc);
+  r = fma(fn, kExpK[2], r);
+  // exp(r), |r| <= ln2/2 : Taylor to degree 13 (truncation 4e-18), Estrin evaluation
+  const double r2 = r * r;
+  const double r4 = r2 * r2;
+  const double r8 = r4 * r4;
+  const double p01 = 1.0 + r;
+  const double p23 = fma(r, kExpC[3], kExpC[2]);
+  const double p45 = fma(r, kExpC[5], kExpC[4]);
+  const double p67 = fma(r, kExpC[7], kExpC[6]);
+  const double p89 = fma(r, kExpC[9], kExpC[8]);
+  const double pab = fma(r, kExpC[11], kExpC[10]);
+  const double pcd = fma(r, kExpC[13], kExpC[12]);
+  const double q0 = fma(r2, p23, p01);
+  const double q1 = fma(r2, p67, p45);
+  const double q2 = fma(r2, pab, p89);
+  const double s0 = fma(r4, q1, q0);
+  const double s1 = fma(r4, pcd, q2);
+  const double p = fma(r8, s1, s0);
+  const double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  if (!CHECKED) return res;
+  return (x <= -708.0) ? 0.0 : ((x != x) ? x : res);
+}
+__device__ __forceinline__ double exp_fast(double x) { return exp_fast_t<true>(x); }
+
+// log(u) for finite normal u >= 1 (the softplus link's 1 + exp(.)); fdlibm's scheme:
+// u = 2^k (1+f), s = f/(2+f), log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)).
+// CHECKED = true propagates NaN.
+template <bool CHECKED>
+__device__ __forceinline__ double log_ge1_fast_t(double u) {
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  int k = (hi >> 20) - 1023;
+  hi &= 0x000fffff;
+  const int i = (hi + 0x95f64) & 0x100000;  // mantissa above sqrt(2): halve it, bump the exponent
+  k += i >> 20;
+  const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
+  const double f = m - 1.0;
+  const double s = f * rcp_fast2(2.0 + f);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * fma(w, fma(w, kLogC[5], kLogC[3]), kLogC[1]);
+  const double t2 = z * fma(w, fma(w, fma(w, kLogC[6], kLogC[4]), kLogC[2]), kLogC[0]);
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)k;
+  const double res = fma(dk, kLogC[7], f - (hfsq - fma(s, hfsq + R, dk * kLogC[8])));
+  if (!CHECKED) return res;
+  return (u != u) ? u : res;
+}
+__device__ __forceinline__ double log_ge1_fast(double u) { return log_ge1_fast_t<true>(u); }
+
+// The reference's link, literally log(1 + exp(g - shift)) (likModulatorNMFPower.m:44 with
+// link = @(g) log(1+exp(g-c))): the rounding of 1 + exp(.) is part of the arithmetic.
+__device__ __forceinline__ double softplus_fast(double xs) {
+  return log_ge1_fast(1.0 + exp_fast(xs));
+}
+// For finite arguments only (no NaN propagation): the moment warps of the sequential passes.
+__device__ __forceinline__ double softplus_fast_finite(double xs) {
+  return log_ge1_fast_t<false>(1.0 + exp_fast_t<false>(xs));
+}
+
+// sqrt(x) for finite normal x > 0 (no zero handling).
+__device__ __forceinline__ double sqrt_fast2_pos(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r;
+  double h = 0.5 * r;
+  const double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, x);
+  return fma(d, h, g);
+}
+
+}  // namespace nsagp

@@ -3,9 +3,9 @@
 // The ADF pass is a nonlinear recurrence: step k cannot start before step k-1
 // has produced its posterior mean, so what matters is the LATENCY of one
 // likModulatorNMFPower evaluation (likModulatorNMFPower.m:28-87), not
-// throughput.  A single warp needs three rounds of 32 sigma points with ~2500
-// dependent-heavy FP64 instructions each.  Here one CTA owns the signal and the
-// S x D work of a step is spread over 4*S threads:
+// throughput.  One CTA owns the signal.  Warp 0 is the "Kalman warp" (lane n owns
+// latent block n); the remaining warps are "moment warps" that spread the S x D
+// work of a step over 4*S threads:
 //
 //   thread (s, dg): sigma point s, subband group dg in 0..3 (d = dg, dg+4, ...)
 //   - link: lanes dg < N evaluate softplus for modulator j = dg, the 4 lanes of a
@@ -13,97 +13,120 @@
 //   - a(s,d), v_s and m_s partials over the thread's DPT subbands, completed over
 //     the 4 lanes with two xor-shuffles;
 //   - pdf / weights once per point (computed by all 4 lanes: SIMT makes it free);
-//   - sums over s: xor-shuffles over the 8 points of a warp, then shared memory
-//     across warps (two barriers).
+//   - y = NaN (missing sample) never reaches these threads: the Kalman warp applies the
+//     reference's NaN semantics itself, so everything here is finite and branch-free;
+//   - sums over the 8 points of a warp by a register-transposing butterfly
+//     (NVP/2 + NVP/4 + NVP/4 shuffles instead of 3 NV), then one shared-memory
+//     row per (warp, dg); the Kalman lanes add the rows they need themselves.
 //
-// When 4*S <= blockDim.x (SINGLE) every thread owns the same sigma point in every
-// step, so its abscissa, weight and rows of W live in registers for the whole pass.
+// The two sides meet at two named barriers per step (producer: bar.arrive,
+// consumer: bar.sync), so the Kalman warp's stores and logarithm overlap the
+// moment warps' work.  All arithmetic on the critical path is straight-line
+// (fastmath.cuh).
+//
+// When 4*S <= (moment threads) (SINGLE) every thread owns the same sigma point in
+// every step, so its abscissa, weight and rows of W live in registers for the pass.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 #include "mom.cuh"
 
 namespace nsagp {
 
+constexpr int kBarCavity = 1;     // Kalman warp -> moment warps: cavity (mu, s2, sd, 1/s2) is in shared memory
+constexpr int kBarSums = 2;       // moment warps -> Kalman warp: partial sums are in shared memory
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int DPT>
 struct MomCta {
   static constexpr int NV = 2 * DPT + 3;          // per-thread sums: a1[DPT] a2[DPT] g1 g2 z
-  // shared-memory doubles needed besides mu/s2: partials [nwarps][4][NV] + finals [4][NV]
-  __host__ __device__ static constexpr int smem_doubles(int nwarps) { return (nwarps + 1) * 4 * NV; }
+  static constexpr int NVP = (NV + 3) & ~3;       // padded to a multiple of 4 for the transposing butterfly
+  static constexpr int kCav = 72;                 // mu[32] s2[32] sd[4] rs2[4]
+  // shared-memory doubles: cavity + partial rows [moment warps][4][NVP]
+  __host__ __device__ static constexpr int smem_doubles(int nmw) { return kCav + nmw * 4 * NVP; }
 };
 
-// Per-thread constants (fixed for the whole pass).
+// Per-thread constants of a moment thread (fixed for the whole pass).
 template <int DPT>
 struct MomCtaThread {
   double W[DPT][kNP];     // rows dg, dg+4, ... of W
   double xn0, wn0;        // SINGLE: this thread's abscissa (modulator jj) and weight (0 if inactive)
   int dg, jj;
-  __device__ __forceinline__ void init(const MomParams& p, int tid) {
-    dg = tid & 3;
+  __device__ __forceinline__ void init(const MomParams& p, int mtid) {
+    dg = mtid & 3;
     jj = dg < p.N ? dg : 0;
+    // Rows beyond D repeat a real row (not zeros): their cavity entries are zero, so they add
+    // nothing to v_s / m_s, and their sums land in slots no Kalman lane reads -- but a = sqrt(.)
+    // stays an ordinary positive number, so the straight-line sqrt needs no zero case.
 #pragma unroll
     for (int i = 0; i < DPT; ++i) {
-      const int d = dg + 4 * i;
+      const int d = (dg + 4 * i) % p.D;
 #pragma unroll
-      for (int j = 0; j < kNP; ++j) W[i][j] = (d < p.D) ? p.W[d * kNP + j] : 0.0;
+      for (int j = 0; j < kNP; ++j) W[i][j] = p.W[d * kNP + j];
     }
-    const int s = tid >> 2;
-    const bool act = s < p.S;
+    const int s = mtid >> 2;
+    const bool act = mtid >= 0 && s < p.S;
     xn0 = act ? p.xn[jj * p.S + s] : 0.0;
     wn0 = act ? p.wn[s] : 0.0;
   }
 };
 
-// All threads of the CTA must call (contains two __syncthreads).  blockDim.x is a
-// multiple of 32.  mu/s2: D+N cavity values in shared memory, written by the caller
-// and made visible by a barrier before the call.  On return s_fin (4*NV doubles)
-// holds the raw sums; use mom_cta_result() to read one site's derivatives.
+// Work of one moment thread for one step.  mtid: index among the moment threads,
+// nmt: their number (multiple of 32).  s_cav: cavity written by the Kalman warp
+// (visible after kBarCavity).  Writes this warp's partial rows to s_part; the
+// caller then arrives at kBarSums.
 template <int DPT, bool SINGLE>
-__device__ __forceinline__ void mom_cta(const MomParams& p, const MomCtaThread<DPT>& th, double alpha, double y,
-                                        const double* mu, const double* s2, double* s_part, double* s_fin) {
-  constexpr int NV = MomCta<DPT>::NV;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+__device__ __forceinline__ void mom_cta_points(const MomParams& p, const MomCtaThread<DPT>& th, double noise, double y,
+                                               const double* s_cav, double* s_part, int mtid, int nmt) {
+  constexpr int NVP = MomCta<DPT>::NVP;
+  const int lane = mtid & 31, mw = mtid >> 5;
   const int dg = th.dg, jj = th.jj;
-  const double noise = p.sn2 / alpha;
-  double acc[NV];
+  double acc[NVP];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  for (int v = 0; v < NVP; ++v) acc[v] = 0.0;
 
-  const double mug = mu[p.D + jj];
-  const double s2g = s2[p.D + jj];
-  const double sdg = sqrt(s2g);                     // NaN for a negative cavity variance (reference goes complex)
-  const double rs2g = 1.0 / s2g;
-  // this thread's subband cavity values
+  const double mug = s_cav[p.D + jj];
+  const double sdg = s_cav[64 + jj];                // sqrt(s2_g)  (likModulatorNMFPower.m:34)
+  const double rs2g = s_cav[68 + jj];               // 1 / s2_g
   double muz[DPT], s2z[DPT];
 #pragma unroll
   for (int i = 0; i < DPT; ++i) {
     const int d = dg + 4 * i;
     const bool in = d < p.D;
-    muz[i] = in ? mu[d] : 0.0;
-    s2z[i] = in ? s2[d] : 0.0;
+    muz[i] = in ? s_cav[d] : 0.0;
+    s2z[i] = in ? s_cav[32 + d] : 0.0;
   }
   const int items = 4 * p.S;
-  const int rounds = SINGLE ? 1 : (items + nthreads - 1) / nthreads;
+  const int rounds = SINGLE ? 1 : (items + nmt - 1) / nmt;
   for (int r = 0; r < rounds; ++r) {
-    const int it = r * nthreads + tid;
+    const int it = r * nmt + mtid;
     const bool act = it < items;
     const int s = act ? (it >> 2) : 0;
     // link (one modulator per lane), then exchange within the 4 lanes of the point
     const double xi = SINGLE ? th.xn0 : p.xn[jj * p.S + s];
-    const double xj = mug + sdg * xi;
-    const double lj = (dg < p.N) ? log(1.0 + exp(xj - p.shift)) : 0.0;     // literal link (parity)
+    const double xj = fma(sdg, xi, mug);
+    // lanes dg >= N repeat modulator 0; their value meets the zero-padded column of W
+    const double lj = softplus_fast_finite(xj - p.shift);
     double l[kNP];
 #pragma unroll
     for (int j = 0; j < kNP; ++j) l[j] = __shfl_sync(0xffffffffu, lj, (lane & ~3) | j);
-    double a[DPT];
+    double a[DPT], a2[DPT];
     double vs = 0.0, ms = 0.0;
 #pragma unroll
     for (int i = 0; i < DPT; ++i) {
       double ad = 0.0;
 #pragma unroll
       for (int j = 0; j < kNP; ++j) ad = fma(l[j], th.W[i][j], ad);
-      if (p.kind == 1) ad = sqrt(ad);
-      a[i] = ad;                                     // padded rows of W are zero -> a = 0
-      vs = fma(ad * ad, s2z[i], vs);
+      if (p.kind == 1) { a2[i] = ad; ad = sqrt_fast2_pos(ad); } // a = sqrt(W link): a.^2 is the argument itself
+      else a2[i] = ad * ad;
+      a[i] = ad;
+      vs = fma(a2[i], s2z[i], vs);
       ms = fma(ad, muz[i], ms);
     }
     vs += __shfl_xor_sync(0xffffffffu, vs, 1);
@@ -111,73 +134,120 @@ __device__ __forceinline__ void mom_cta(const MomParams& p, const MomCtaThread<D
     vs += __shfl_xor_sync(0xffffffffu, vs, 2);
     ms += __shfl_xor_sync(0xffffffffu, ms, 2);
     const double v = noise + vs;
-    const double rv = 1.0 / v;
-    const double rsd = rsqrt(v);
+    const double rv = rcp_fast2(v);
+    const double rsd = rsqrt_fast2(v);
     const double res = y - ms;
     const double t = res * rsd;
-    const double pdf = exp(-0.5 * (t * t)) * (rsd * kInvSqrt2Pi);
+    const double pdf = exp_fast_t<false>(-0.5 * (t * t)) * (rsd * kInvSqrt2Pi);
     const double wgt = SINGLE ? th.wn0 : (act ? p.wn[s] : 0.0);
-    const double wp = act ? wgt * pdf : 0.0;         // inactive threads contribute exact zeros
+    const double wp = wgt * pdf;                     // inactive threads: weight 0, finite pdf
     const double q = res * rv;
     const double c1 = wp * q;
-    const double c2 = wp * (q * q - rv);
-    if (act) {
+    const double c2 = wp * fma(q, q, -rv);
 #pragma unroll
-      for (int i = 0; i < DPT; ++i) {
-        acc[i] = fma(a[i], c1, acc[i]);
-        acc[DPT + i] = fma(a[i] * a[i], c2, acc[DPT + i]);
-      }
-      if (dg < p.N) {
-        const double e = (xj - mug) * rs2g;
-        acc[2 * DPT] = fma(wp, e, acc[2 * DPT]);
-        acc[2 * DPT + 1] = fma(wp, e * e - rs2g, acc[2 * DPT + 1]);
-      }
-      if (dg == 0) acc[2 * DPT + 2] += wp;
+    for (int i = 0; i < DPT; ++i) {
+      acc[i] = fma(a[i], c1, acc[i]);
+      acc[DPT + i] = fma(a2[i], c2, acc[DPT + i]);
+    }
+    // (rows dg >= N of the g-sums and rows dg > 0 of Z are never read)
+    const double e = (xj - mug) * rs2g;
+    acc[2 * DPT] = fma(wp, e, acc[2 * DPT]);
+    acc[2 * DPT + 1] = fma(wp, fma(e, e, -rs2g), acc[2 * DPT + 1]);
+    acc[2 * DPT + 2] += wp;
+  }
+  // Sums over the 8 points of this warp (lanes with equal dg: xor 16, 8, 4).
+  // Level 1 and 2 halve the number of live values (each lane keeps the half selected
+  // by its own bit and receives the partner's copy of it); level 3 is a plain butterfly.
+  constexpr int H = NVP / 2, Qn = NVP / 4;
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const double send = up ? acc[i] : acc[i + H];
+      const double keep = up ? acc[i + H] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
   }
-  // sums over the 8 points of this warp (lanes with equal dg)
+  {
+    const bool up = (lane & 8) != 0;
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    double x = acc[v];
-    x += __shfl_xor_sync(0xffffffffu, x, 4);
-    x += __shfl_xor_sync(0xffffffffu, x, 8);
-    x += __shfl_xor_sync(0xffffffffu, x, 16);
-    acc[v] = x;
+    for (int i = 0; i < Qn; ++i) {
+      const double send = up ? acc[i] : acc[i + Qn];
+      const double keep = up ? acc[i + Qn] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
   }
-  if (lane < 4) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) s_part[(warp * 4 + lane) * NV + v] = acc[v];
+  for (int i = 0; i < Qn; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+  if ((lane & 4) == 0) {
+    // this lane holds entries j0 .. j0+Qn-1 of row (mw, dg)
+    const int j0 = ((lane >> 4) & 1) * H + ((lane >> 3) & 1) * Qn;
+    double* row = s_part + (mw * 4 + dg) * NVP + j0;
+#pragma unroll
+    for (int i = 0; i < Qn; ++i) row[i] = acc[i];
   }
-  __syncthreads();
-  if (tid < 4 * NV) {
-    const int nw = nthreads >> 5;
-    double x = 0.0;
-    for (int w = 0; w < nw; ++w) x += s_part[w * 4 * NV + tid];
-    s_fin[tid] = x;
-  }
-  __syncthreads();
 }
 
-// Derivatives for site n from the raw sums (likModulatorNMFPower.m:55-80).  pep is
-// pep_const(kind, sn2, alpha), a per-pass constant the caller computes once.
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// Kalman lane n: shared-memory byte addresses (first moment warp's rows) of the three sums
+// of its site:  Zs = sum_s w_s N_s,  r1 = sum_s w_s N_s [.]',  r2 = sum_s w_s N_s [.]''
+// (likModulatorNMFPower.m:55-80).
 template <int DPT>
-__device__ __forceinline__ void mom_cta_result(const MomParams& p, double pep, const double* s_fin, int n,
-                                               double& Z, double& d1, double& d2) {
-  constexpr int NV = MomCta<DPT>::NV;
-  Z = pep * fmax(s_fin[2 * DPT + 2], kJitter);      // fmax(NaN, jitter) = jitter, as MATLAB max
-  const double zp = (1.0 / Z) * pep;
-  double r1, r2;
-  if (n < p.D) {
-    const int dg = n & 3, i = n >> 2;
-    r1 = s_fin[dg * NV + i];
-    r2 = s_fin[dg * NV + DPT + i];
-  } else {
-    const int j = n - p.D;
-    r1 = s_fin[j * NV + 2 * DPT];
-    r2 = s_fin[j * NV + 2 * DPT + 1];
+struct MomCtaSumAddr {
+  unsigned z, a, b;
+  __device__ __forceinline__ void init(const double* s_part, int n, int D) {
+    constexpr int NVP = MomCta<DPT>::NVP;
+    int dg, j1, j2;
+    if (n < D) { dg = n & 3; j1 = n >> 2; j2 = DPT + (n >> 2); }
+    else { dg = n - D; j1 = 2 * DPT; j2 = 2 * DPT + 1; }
+    const unsigned base = (unsigned)__cvta_generic_to_shared(s_part);
+    z = base + 8u * (2 * DPT + 2);                  // row dg = 0
+    a = base + 8u * (dg * NVP + j1);
+    b = base + 8u * (dg * NVP + j2);
   }
-  d1 = zp * r1;
-  d2 = -d1 * d1 + zp * r2;
+};
+
+// Add the rows of the nmw moment warps (two accumulators per sum: shorter chain).
+template <int DPT>
+__device__ __forceinline__ void mom_cta_sums(const MomCtaSumAddr<DPT>& ad, int nmw, double& Zs, double& r1, double& r2) {
+  constexpr unsigned kRow = 4u * MomCta<DPT>::NVP * 8u;    // bytes between consecutive warps' rows
+  double z0 = 0.0, z1 = 0.0, a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  unsigned o = 0;
+  int w = 0;
+#pragma unroll 5
+  for (; w + 1 < nmw; w += 2, o += 2 * kRow) {
+    z0 += lds_f64(ad.z + o); z1 += lds_f64(ad.z + o + kRow);
+    a0 += lds_f64(ad.a + o); a1 += lds_f64(ad.a + o + kRow);
+    b0 += lds_f64(ad.b + o); b1 += lds_f64(ad.b + o + kRow);
+  }
+  if (w < nmw) { z0 += lds_f64(ad.z + o); a0 += lds_f64(ad.a + o); b0 += lds_f64(ad.b + o); }
+  Zs = z0 + z1; r1 = a0 + a1; r2 = b0 + b1;
+}
+
+// Damped ADF site update from the raw sums, with a single reciprocal:
+//   dlZ = r1/Zm, d2lZ = -dlZ^2 + r2/Zm, Zm = max(Zs, jitter)           (likModulatorNMFPower.m:55-80)
+//   ttau_new = -d2lZ / (1 + d2lZ s2) = -Nn / (Zm^2 + Nn s2),  Nn = r2 Zm - r1^2
+//   tnu_new  = (dlZ - mu d2lZ) / (1 + d2lZ s2) = (r1 Zm - mu Nn) / (Zm^2 + Nn s2)
+// (ihgp_ep_modulator_nmf.m:265-266, gf_ep_modulator_nmf.m:147-148).
+__device__ __forceinline__ void adf_site_from_sums(double Zs, double r1, double r2, double mu, double s2,
+                                                   double& tt_new, double& tn_new, double& Zm) {
+  Zm = fmax(Zs, kJitter);                           // fmax(NaN, jitter) = jitter, as MATLAB max
+  const double Nn = fma(r2, Zm, -r1 * r1);
+  const double den = fma(Nn, s2, Zm * Zm);
+  const double num_t = fma(r1, Zm, -mu * Nn);
+  if (fabs(den) > 1e-280 && fabs(den) < 1e280) {    // ordinary number: straight-line reciprocal
+    const double rd = rcp_fast2(den);
+    tt_new = -Nn * rd;
+    tn_new = num_t * rd;
+  } else {                                          // 0, Inf, NaN: IEEE division semantics
+    tt_new = -Nn / den;
+    tn_new = num_t / den;
+  }
 }
 
 }  // namespace nsagp

@@ -244,7 +244,7 @@ def _predict_outputs(plan, mdl, return_ind, nargout, debug_cov):
 
 
 def _run(kind, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction, ep_damping, ep_itts,
-         constrained, balance, nargout, debug_cov, nlz_mode=_lib.MODE_NLZ):
+         constrained, balance, nargout, debug_cov, nlz_mode=_lib.MODE_NLZ, adf_form=0):
     mom = _require_moments(mom)
     yall, return_ind = merge_inputs(x, y, xt)
     if constrained is None:
@@ -262,6 +262,7 @@ def _run(kind, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_
               tables=tabs) as plan:
         if predict and debug_cov and kind == _lib.KIND_FULL and nargout > 5:
             plan.keep_pf()
+        plan.set_adf_form(adf_form)
         plan.run()
         if predict:
             res = _predict_outputs(plan, mdl, return_ind, nargout, debug_cov)
@@ -275,34 +276,34 @@ def _run(kind, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_
 
 # ---------------------------------------------------------------- entry points
 def gf_ep_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
-                        ep_fraction, ep_damping, ep_itts, nargout=6, debug_cov=False):
+                        ep_fraction, ep_damping, ep_itts, nargout=6, debug_cov=False, adf_form=0):
     """Solve the time-frequency-NMF GP model by Power EP (full-state Kalman filter /
     RTS smoother).  Drop-in for matlab/gf_ep_modulator_nmf.m."""
     return _run(_lib.KIND_FULL, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
-                ep_damping, ep_itts, None, False, nargout, debug_cov)
+                ep_damping, ep_itts, None, False, nargout, debug_cov, adf_form=adf_form)
 
 
 def gf_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
                                     ep_fraction, ep_damping, ep_itts, constraints, w_fixed, tune_hypers,
-                                    nargout=6, debug_cov=False):
+                                    nargout=6, debug_cov=False, adf_form=0):
     """matlab/gf_ep_modulator_nmf_constraints.m: box-constrained parameters, balanced model."""
     return _run(_lib.KIND_FULL, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
-                ep_damping, ep_itts, (constraints, w_fixed, tune_hypers), True, nargout, debug_cov)
+                ep_damping, ep_itts, (constraints, w_fixed, tune_hypers), True, nargout, debug_cov, adf_form=adf_form)
 
 
 def ihgp_ep_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
-                          ep_fraction, ep_damping, ep_itts, nargout=6):
+                          ep_fraction, ep_damping, ep_itts, nargout=6, adf_form=0):
     """Power EP with the infinite-horizon (steady-state gain) approximation.
     Drop-in for matlab/ihgp_ep_modulator_nmf.m."""
     return _run(_lib.KIND_IHGP, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
-                ep_damping, ep_itts, None, True, nargout, False)
+                ep_damping, ep_itts, None, True, nargout, False, adf_form=adf_form)
 
 
 def ihgp_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
                                       ep_fraction, ep_damping, ep_itts, constraints, w_fixed, tune_hypers,
-                                      nargout=6):
+                                      nargout=6, adf_form=0):
     """matlab/ihgp_ep_modulator_nmf_constraints.m (its nlZ mode carries the site
     vectors from step to step, :568-615)."""
     return _run(_lib.KIND_IHGP, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
                 ep_damping, ep_itts, (constraints, w_fixed, tune_hypers), True, nargout, False,
-                nlz_mode=_lib.MODE_NLZ_RUNNING)
+                nlz_mode=_lib.MODE_NLZ_RUNNING, adf_form=adf_form)

@@ -30,13 +30,14 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("adf_form", [0, 1])      # one CTA per signal / one warp per signal
 @pytest.mark.parametrize("D,N,T,k1,k2,kind,p,shift,alpha,itts,gaps", CASES)
-def test_ihgp_predict_matches_oracle(nsagp, gpu_lib, D, N, T, k1, k2, kind, p, shift, alpha, itts, gaps):
+def test_ihgp_predict_matches_oracle(nsagp, gpu_lib, D, N, T, k1, k2, kind, p, shift, alpha, itts, gaps, adf_form):
     from oracle import ihgp_ep
     pb = make_problem(nsagp, D, N, T, k1, k2, seed=11 + D + T, kind=kind, p=p, shift=shift, gaps=gaps)
     damping = np.linspace(0.5, 0.3, itts)
     Eo, Vo, _, lbo, ubo, oo = ihgp_ep.ihgp_ep_modulator_nmf(*_args(pb, "ref", pb["t"], alpha, damping, itts))
-    Eg, Vg, Cg, lbg, ubg, og = nsagp.ihgp_ep_modulator_nmf(*_args(pb, "gpu", pb["t"], alpha, damping, itts))
+    Eg, Vg, Cg, lbg, ubg, og = nsagp.ihgp_ep_modulator_nmf(*_args(pb, "gpu", pb["t"], alpha, damping, itts), adf_form=adf_form)
     assert Cg is None
     tol = TOL_SEQ if itts == 1 else TOL_SCAN
     assert rel_err(og["nlZ"], oo["nlZ"]) < tol

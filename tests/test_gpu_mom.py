@@ -98,3 +98,52 @@ def test_mom_jitter_floor(nsagp, gpu_lib):
     for wf in (False, True):
         lZ, d1, d2 = mom.batch(np.log([1e-4]), y, mu, s2, W, 1.0, warp_form=wf)
         assert np.allclose(lZ, np.log(1e-10), rtol=0, atol=1e-12)
+
+
+# ---- straight-line FP64 routines of the sequential passes (csrc/fastmath.cuh) ----
+def _fast(gpu_lib, nsagp, op, x):
+    x = np.ascontiguousarray(x, float)
+    out = np.empty_like(x)
+    nsagp._lib.check(gpu_lib.nsagp_fastmath_eval(op, x.size, nsagp._lib.dptr(x), nsagp._lib.dptr(out)))
+    return out
+
+
+def _ulps(a, b):
+    return np.max(np.abs(a - b) / np.spacing(np.abs(b)))
+
+
+def test_fastmath_accuracy(nsagp, gpu_lib):
+    rng = np.random.default_rng(0)
+    pos = np.exp(rng.uniform(np.log(1e-250), np.log(1e250), 200000))
+    sgn = np.where(rng.random(pos.size) < 0.5, -1.0, 1.0)
+    ld = np.longdouble
+    ref_rsqrt = (1.0 / np.sqrt(pos.astype(ld))).astype(float)
+    u_rcp = [_ulps(_fast(gpu_lib, nsagp, op, pos * sgn), 1.0 / (pos * sgn)) for op in (0, 6)]
+    u_rsq = [_ulps(_fast(gpu_lib, nsagp, op, pos), ref_rsqrt) for op in (1, 7)]
+    u_sqr = [_ulps(_fast(gpu_lib, nsagp, op, pos), np.sqrt(pos)) for op in (2, 8)]
+    print("ulps rcp %s rsqrt %s sqrt %s (full, one Newton step fewer)" % (u_rcp, u_rsq, u_sqr))
+    assert u_rcp[0] <= 2 and u_rsq[0] <= 2 and u_sqr[0] <= 2
+    assert u_rcp[1] <= 2 and u_rsq[1] <= 2 and u_sqr[1] <= 2        # the variants the moment warps use
+    assert _fast(gpu_lib, nsagp, 2, np.zeros(3)).tolist() == [0.0, 0.0, 0.0]
+    assert _fast(gpu_lib, nsagp, 8, np.zeros(3)).tolist() == [0.0, 0.0, 0.0]
+    xe = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-2, 2, 100000), [0.0, -707.9, 708.9]])
+    assert _ulps(_fast(gpu_lib, nsagp, 3, xe), np.exp(xe.astype(ld)).astype(float)) <= 2
+    assert np.all(_fast(gpu_lib, nsagp, 3, np.array([-708.0, -745.0, -1e4, -np.inf])) == 0.0)
+    big = _fast(gpu_lib, nsagp, 3, np.array([709.5, 1000.0, np.inf, np.nan]))
+    assert np.all(np.isfinite(big[:3])) and np.all(big[:3] > 8e307) and np.isnan(big[3])   # saturates, NaN propagates
+    u = np.concatenate([1.0 + np.exp(rng.uniform(-40, 40, 200000)), rng.uniform(1, 3, 100000), [1.0, 2.0 ** 0.5, 2.0]])
+    lg = _fast(gpu_lib, nsagp, 4, u)
+    ref = np.log(u.astype(ld)).astype(float)
+    nz = ref != 0
+    assert np.max(np.abs(lg[nz] - ref[nz]) / np.abs(ref[nz])) < 1e-15
+    assert np.all(lg[~nz] == 0.0)
+    assert np.isnan(_fast(gpu_lib, nsagp, 4, np.array([np.nan]))[0])
+    # the link literally: log(1 + exp(x)), including the rounding of 1 + exp(x); the reference
+    # value is built from the GPU's own exp (1 ulp of exp moves log(1+exp) by up to 1e-13 relative)
+    xs = rng.uniform(-60, 60, 200000)
+    ex = _fast(gpu_lib, nsagp, 3, xs)
+    lit = np.log((1.0 + ex).astype(ld)).astype(float)
+    sp = _fast(gpu_lib, nsagp, 5, xs)
+    nz = lit != 0
+    assert np.max(np.abs(sp[nz] - lit[nz]) / np.abs(lit[nz])) < 1e-15
+    assert np.all(sp[~nz] == 0.0)
