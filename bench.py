@@ -17,9 +17,9 @@ region and reported as setup_s.
   value : device-timed, model/tables/signal already resident in HBM
   e2e   : the same run through the C ABI call nsagp_ep_ihgp with HOST buffers
           (H2D of signal+model+tables, D2H of Eft/Varft/lb/ub inside the timed region)
-  --impl reference : the oracle restatement of the reference's MATLAB loop on the
-          host cores (the reference itself cannot run: no MATLAB/Octave), one
-          independent clip per core, bounded sample.
+  --impl reference : the reference's MATLAB loop restated in plain C (oracle/c, same
+          dense operations; the reference itself cannot run: no MATLAB/Octave) on all
+          host cores, one independent clip per core, bounded sample.
 """
 import argparse
 import importlib
@@ -40,6 +40,8 @@ D, N, T_FULL = 16, 3, 100000
 K1, K2 = "exp", "matern52"
 ALPHA, SHIFT, P_CUB = 0.75, 1.0, 9
 EP_ITTS = 20
+# DRAM bytes per time step of the ADF kernel from the committed ncu --set full capture (profiles/); None = not captured
+TRAFFIC_ADF_BYTES_PER_STEP = None
 WORKLOAD = ("C2: ihgp_ep_modulator_nmf predict mode, D=16 exp subbands x N=3 matern52 modulators (n=41), "
             "likModulatorPreCalcwn p=9 (S=77), alpha=0.75, ep_itts=20, T=100000, 1 signal per GPU")
 
@@ -114,37 +116,37 @@ class ClockSampler:
 
 # ----------------------------------------------------------------- CPU arms
 def _oracle_clip(args):
-    """One independent clip through the oracle (runs in a worker process)."""
+    """One independent clip through the CPU port (runs in a worker process).  The port is
+    oracle/c/nsagp_oracle.c: the reference's MATLAB loop restated in plain C with the same dense
+    n-by-n operations (the reference itself cannot run: no MATLAB/Octave here or on the GPU box).
+    Model construction and the DARE tables are excluded from the timed region, as on the GPU side."""
     seed, T, itts = args
     nsagp = importlib.import_module(PKG)
-    from oracle import cubature as ocub, ihgp_ep, lik as olik, ssmodel as oss
+    from oracle import c_oracle, cubature as ocub, ihgp_ep, ssmodel as oss
     hyp, y = make_signal(nsagp, seed, T)
     wo, xo = ocub.utp_ws(P_CUB, N)
-    mom = olik.make_mom("precalc", olik.softplus_link(SHIFT), wn=wo, xn_unscaled=xo)
     ss = lambda x, p1, p2, k1, k2: oss.ss_modulators_nmf(p1, p2, k1, k2)
     t = np.arange(1.0, T + 1.0)
-    # setup (model + tables) is excluded from the timed loops, as on the GPU side
     lik_param, param1, param2, Wnmf = oss.unpack_log(hyp.pack_log(), 1, D, N)
     A, Q, H, Pinf = ihgp_ep._model(lik_param, param1, param2, ss, t, K1, K2)
     tabs = ihgp_ep.ihgp_setup(A, Q, H)
+    prob = c_oracle.IhgpProblem(A, H, Pinf, tabs, 1, lik_param, SHIFT, Wnmf, wo, xo, ALPHA, damping(itts), itts)
     t0 = time.perf_counter()
-    ihgp_ep.ihgp_ep_core(A, tabs["Q"], H, Pinf, lik_param, Wnmf, y, mom, ALPHA, damping(itts), itts,
-                         np.arange(T), tabs=tabs)
+    prob.predict(y)
     return time.perf_counter() - t0
 
 
 def cpu_arm(steps, warmup, T_sample, itts, cores):
-    """Oracle port on `cores` host cores, one clip per core per step."""
+    """CPU port on `cores` host cores, one independent clip per core per step.  Returns
+    (time-steps/s over the timed region of the slowest core, seconds per step)."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     times = []
     with ctx.Pool(cores) as pool:
         for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            pool.map(_oracle_clip, [(1000 + 17 * it + c, T_sample, itts) for c in range(cores)])
-            dt = time.perf_counter() - t0
+            per_clip = pool.map(_oracle_clip, [(1000 + 17 * it + c, T_sample, itts) for c in range(cores)])
             if it >= warmup:
-                times.append(dt)
+                times.append(max(per_clip))
     per_step = float(np.mean(times))
     return cores * T_sample * itts / per_step, per_step
 
@@ -154,15 +156,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    T_sample, itts = 150, EP_ITTS
+    T_sample, itts = 600, EP_ITTS
     value, per_step = cpu_arm(args.steps, args.warmup, T_sample, itts, cores)
-    sample = "%d independent clips (one per core) of T=%d, ep_itts=%d per step; NumPy oracle port" % (cores, T_sample, itts)
+    sample = ("%d independent clips (one per host core) of T=%d, ep_itts=%d per step; plain-C port of "
+              "matlab/ihgp_ep_modulator_nmf.m (oracle/c/nsagp_oracle.c), model/table setup untimed" % (cores, T_sample, itts))
     line = {"impl": "reference", "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value,
             "unit": "time-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference = MATLAB; MATLAB/Octave absent, so the oracle "
-                       "restatement of matlab/ihgp_ep_modulator_nmf.m is timed on the host cores"},
+            "config": {"workload": WORKLOAD, "note": "the reference is MATLAB; MATLAB/Octave are absent here and on the "
+                       "GPU box, so its loop restated in C (same dense operations) is timed on the host cores"},
             "cpu_baseline": {"value": value, "unit": "time-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "time-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -291,13 +294,15 @@ def run_gpu(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         n, M = mdl.n, mdl.M
-        # dominant kernel: the sequential ADF filter pass (ihgp_adf_kernel), one launch per run.
-        # algorithmic bytes per step of that pass: read y (8) + write ttau,tnu,R (24M) + write MS (8n) + write lZ (8)
-        adf_bytes = T * (8 + 24 * M + 8 * n + 8)
+        # Dominant kernel: ihgp_adf_cta_kernel, the sequential ADF filter pass (one launch per run).
+        # Algorithmic bytes per time step of that pass: read y (8) and the old
+        # sites ttau,tnu (16M); write ttau,tnu,R (24M), the filtered mean (8n) and lZ (8).
+        adf_bytes = T * (8 + 16 * M + 24 * M + 8 * n + 8)
         adf_ms = phase["adf"] / args.steps
         ach = adf_bytes / (adf_ms * 1e-3) / 1e9 if adf_ms > 0 else 0.0
         # whole-run figure with SURVEY 8d's per-step-per-sweep bytes (8 + 24n + 88M)
         sweep_bytes = (8 + 24 * n + 88 * M) * T * itts
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         line = {
             "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value, "unit": "time-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -310,10 +315,14 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(d2h), "call": "nsagp_ep_ihgp (C ABI, host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ihgp_adf_kernel (sequential ADF filter pass, 1 warp per signal)",
+            "roofline": {"bound": "hbm", "kernel": "ihgp_adf_cta_kernel (sequential ADF filter pass, one CTA per signal)",
                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "latency-bound nonlinear recurrence: one step cannot start before the previous ends",
+                         "traffic": TRAFFIC_ADF_BYTES_PER_STEP * T / 1e9 if TRAFFIC_ADF_BYTES_PER_STEP else None,
+                         "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/)",
+                         "peak_source": peak_src,
+                         "note": "the pass is a nonlinear recurrence in time (step k needs the posterior of step k-1), "
+                                 "so it is bound by the latency of one step on one SM, not by HBM: see cycles_per_time_step",
+                         "cycles_per_time_step": adf_ms * 1e-3 * sm_hz / T if adf_ms > 0 else None,
                          "whole_run_GBps": sweep_bytes / (dev_ms / args.steps * 1e-3) / 1e9},
             "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
             "adf_only_steps_per_s": T / (adf_ms * 1e-3) if adf_ms > 0 else None,
@@ -323,10 +332,11 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = 1
-            Tc, ic = 400, 6
+            Tc, ic = 4000, EP_ITTS
             v, per = cpu_arm(1, 0, Tc, ic, cores)
             line["cpu_baseline"] = {"value": v, "unit": "time-steps/s", "cores": cores, "kind": "port",
-                                    "sample": "NumPy oracle of matlab/ihgp_ep_modulator_nmf.m, same model, T=%d ep_itts=%d (%.1f s)" % (Tc, ic, per)}
+                                    "sample": "plain-C port of matlab/ihgp_ep_modulator_nmf.m (oracle/c/nsagp_oracle.c, same dense "
+                                              "operations), same model, T=%d ep_itts=%d, 1 core (%.1f s)" % (Tc, ic, per)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

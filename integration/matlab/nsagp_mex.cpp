@@ -1,0 +1,150 @@
+// nsagp_mex.cpp -- thin MEX gateway from MATLAB to the C ABI of libnsagp.so (include/nsagp.h).
+//
+// Build (on a machine with MATLAB and the CUDA library built by __graft_entry__.build()):
+//   mex -R2018a CXXFLAGS='$CXXFLAGS -std=c++17' -I<repo>/include nsagp_mex.cpp ...
+//       -L<repo>/nonstationary-audio-gp_b200/csrc -lnsagp
+// It cannot be linked in the build container (no MATLAB); `make -C integration/matlab check`
+// compiles it against integration/matlab/stub/mex.h to keep it syntactically honest.
+//
+// Call forms (used by the .m wrappers in this directory, which keep the reference's
+// entry-point names and argument lists):
+//   out = nsagp_mex('ep_ihgp', model, lik, ep, tables, yall, mode)
+//   out = nsagp_mex('ep_full', model, lik, ep, [],     yall, mode)
+//   [lZ, dlZ, d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)
+// model  : struct with fields D, N, bz, bg, A, Q, Pinf, h   (packed per-latent blocks, see nsagp_model)
+// lik    : struct with fields kind, sn2, link_shift, W (D-by-N), wn (1-by-S), xn (N-by-S)
+// ep     : struct with fields ep_fraction, ep_damping (vector), ep_itts
+// tables : struct with fields r (1-by-nr), PP, PG (packed, see nsagp_tables); PG may be []
+// mode   : 0 predict, 1 nlZ, 2 nlZ with running sites (ihgp ..._constraints)
+// out    : struct; predict mode: Eft, Varft, lb, ub, ttau, tnu, R, lZ, MF, MS, nlZ, maxDiffM,
+//          maxDiffP, n_negcav (and PS for 'ep_full'); nlZ modes: edata, ttau, tnu, R, lZ.
+// The gateway only reads mxGetDoubles pointers and writes into mxCreateDoubleMatrix outputs:
+// MATLAB owns every array, the library owns every device buffer.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+#include "nsagp.h"
+
+namespace {
+
+const mxArray* field(const mxArray* s, const char* name, bool required = true) {
+  const mxArray* f = mxIsStruct(s) ? mxGetField(s, 0, name) : nullptr;
+  if (!f && required) mexErrMsgIdAndTxt("nsagp:arg", "missing struct field '%s'", name);
+  return f;
+}
+
+const double* dbl(const mxArray* a, const char* what) {
+  if (!a || mxIsEmpty(a)) return nullptr;
+  if (!mxIsDouble(a) || mxIsComplex(a)) mexErrMsgIdAndTxt("nsagp:arg", "%s must be a real double array", what);
+  return mxGetDoubles(a);
+}
+
+double scalar(const mxArray* s, const char* name) { return mxGetScalar(field(s, name)); }
+
+void fill_model(const mxArray* m, nsagp_model* out) {
+  out->D = (int32_t)scalar(m, "D"); out->N = (int32_t)scalar(m, "N");
+  out->bz = (int32_t)scalar(m, "bz"); out->bg = (int32_t)scalar(m, "bg");
+  out->A = dbl(field(m, "A"), "model.A"); out->Q = dbl(field(m, "Q"), "model.Q");
+  out->Pinf = dbl(field(m, "Pinf"), "model.Pinf"); out->h = dbl(field(m, "h"), "model.h");
+}
+
+void fill_lik(const mxArray* l, nsagp_lik* out) {
+  out->kind = (int32_t)scalar(l, "kind"); out->sn2 = scalar(l, "sn2"); out->link_shift = scalar(l, "link_shift");
+  out->W = dbl(field(l, "W"), "lik.W");
+  out->S = (int32_t)mxGetNumberOfElements(field(l, "wn"));
+  out->wn = dbl(field(l, "wn"), "lik.wn"); out->xn = dbl(field(l, "xn"), "lik.xn");
+}
+
+void check(int status) {
+  if (status == NSAGP_OK) return;
+  const char* id = status == NSAGP_ERR_NOT_PD ? "nsagp:notPD" : status == NSAGP_ERR_NONPOS_VAR ? "nsagp:nonposVar"
+                 : status == NSAGP_ERR_NAN ? "nsagp:nan" : status == NSAGP_ERR_CUDA ? "nsagp:cuda" : "nsagp:invalid";
+  mexErrMsgIdAndTxt(id, "%s", nsagp_last_error());
+}
+
+mxArray* put(mxArray* s, const char* name, mwSize r, mwSize c, double** ptr) {
+  mxArray* a = mxCreateDoubleMatrix(r, c, mxREAL);
+  mxAddField(s, name);
+  mxSetField(s, 0, name, a);
+  *ptr = mxGetDoubles(a);
+  return a;
+}
+
+void ep_call(bool ihgp, int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs != 7) mexErrMsgIdAndTxt("nsagp:arg", "usage: out = nsagp_mex(cmd, model, lik, ep, tables, yall, mode)");
+  (void)nlhs;
+  nsagp_model model; nsagp_lik lik; nsagp_ep ep; nsagp_tables tab;
+  fill_model(prhs[1], &model);
+  fill_lik(prhs[2], &lik);
+  ep.ep_fraction = scalar(prhs[3], "ep_fraction");
+  ep.ep_itts = (int32_t)scalar(prhs[3], "ep_itts");
+  ep.ep_damping = dbl(field(prhs[3], "ep_damping"), "ep.ep_damping");
+  if ((int)mxGetNumberOfElements(field(prhs[3], "ep_damping")) < ep.ep_itts)
+    mexErrMsgIdAndTxt("nsagp:arg", "ep_damping needs ep_itts entries (it is indexed by itt+1)");
+  if (ihgp) {
+    tab.nr = (int32_t)mxGetNumberOfElements(field(prhs[4], "r"));
+    tab.r = dbl(field(prhs[4], "r"), "tables.r");
+    tab.PP = dbl(field(prhs[4], "PP"), "tables.PP");
+    tab.PG = dbl(field(prhs[4], "PG", false), "tables.PG");
+  }
+  const double* y = dbl(prhs[5], "yall");
+  const int64_t T = (int64_t)mxGetNumberOfElements(prhs[5]);
+  const int32_t mode = (int32_t)mxGetScalar(prhs[6]);
+  const mwSize M = model.D + model.N, n = model.D * model.bz + model.N * model.bg;
+  const mwSize nb = model.D * model.bz * model.bz + model.N * model.bg * model.bg;
+
+  mxArray* s = mxCreateStructMatrix(1, 1, 0, nullptr);
+  nsagp_outputs o;
+  std::memset(&o, 0, sizeof(o));
+  put(s, "ttau", M, T, &o.ttau); put(s, "tnu", M, T, &o.tnu); put(s, "R", M, T, &o.R); put(s, "lZ", 1, T, &o.lZ);
+  int64_t negcav = 0;
+  if (mode == NSAGP_MODE_PREDICT) {
+    put(s, "Eft", M, T, &o.Eft); put(s, "Varft", M, T, &o.Varft); put(s, "lb", M, T, &o.lb); put(s, "ub", M, T, &o.ub);
+    put(s, "MF", n, T, &o.MF); put(s, "MS", n, T, &o.MS);
+    put(s, "nlZ", 1, ep.ep_itts, &o.nlZ); put(s, "maxDiffM", 1, ep.ep_itts, &o.maxDiffM);
+    put(s, "maxDiffP", 1, ep.ep_itts, &o.maxDiffP);
+    if (!ihgp) put(s, "PS", nb, T, &o.PS);
+    o.n_negcav = &negcav;
+  } else {
+    put(s, "edata", 1, 1, &o.edata);
+  }
+  check(ihgp ? nsagp_ep_ihgp(&model, &lik, &ep, &tab, y, T, mode, &o) : nsagp_ep_full(&model, &lik, &ep, y, T, mode, &o));
+  if (mode == NSAGP_MODE_PREDICT) {
+    double* p;
+    put(s, "n_negcav", 1, 1, &p);
+    *p = (double)negcav;
+  }
+  plhs[0] = s;
+}
+
+void mom_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: [lZ,dlZ,d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)");
+  nsagp_lik lik;
+  fill_lik(prhs[1], &lik);
+  const int32_t D = (int32_t)mxGetScalar(prhs[2]), N = (int32_t)mxGetScalar(prhs[3]);
+  const int64_t T = (int64_t)mxGetNumberOfElements(prhs[5]);
+  mxArray* lZ = mxCreateDoubleMatrix(1, T, mxREAL);
+  mxArray* d1 = mxCreateDoubleMatrix(D + N, T, mxREAL);
+  mxArray* d2 = mxCreateDoubleMatrix(D + N, T, mxREAL);
+  check(nsagp_mom_batch(&lik, D, N, mxGetScalar(prhs[4]), T, dbl(prhs[5], "y"), dbl(prhs[6], "mu"), dbl(prhs[7], "s2"),
+                        mxGetDoubles(lZ), mxGetDoubles(d1), mxGetDoubles(d2)));
+  plhs[0] = lZ;
+  if (nlhs > 1) plhs[1] = d1; else mxDestroyArray(d1);
+  if (nlhs > 2) plhs[2] = d2; else mxDestroyArray(d2);
+}
+
+}  // namespace
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("nsagp:arg", "first argument must be a command string");
+  char cmd[32];
+  mxGetString(prhs[0], cmd, sizeof(cmd));
+  const std::string c(cmd);
+  if (c == "ep_ihgp") ep_call(true, nlhs, plhs, nrhs, prhs);
+  else if (c == "ep_full") ep_call(false, nlhs, plhs, nrhs, prhs);
+  else if (c == "mom") mom_call(nlhs, plhs, nrhs, prhs);
+  else if (c == "version") plhs[0] = mxCreateString(nsagp_version());
+  else mexErrMsgIdAndTxt("nsagp:arg", "unknown command '%s'", cmd);
+}

@@ -86,40 +86,28 @@ __device__ __forceinline__ double sqrt_fast2(double x) {
   return (x == 0.0) ? 0.0 : g;
 }
 
-// Polynomial coefficients live in constant memory so that they are instruction operands
-// (c[bank][offset]) instead of being re-materialised into registers in every step.
-__constant__ double kExpC[14] = {
-    1.0, 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,
-    1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0};
-__constant__ double kExpK[4] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
-                                6755399441055744.0};      // log2(e), -ln2_hi, -ln2_lo, 1.5 * 2^52
-__constant__ double kLogC[9] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
-                                2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
-                                1.479819860511658591e-01,   // fdlibm Lg1..Lg7
-                                6.93147180369123816490e-01, 1.90821492927058770002e-10};   // ln2_hi, ln2_lo
-
 // exp(x), straight-line, for finite x.  The argument is clamped to [-708, 709]: below, the
 // result is exp(-708) = 3.3e-308 instead of a subnormal or 0; above, exp(709) = 8.2e307 instead
 // of Inf.  CHECKED = true additionally returns exactly 0 below -708 and propagates NaN.
 template <bool CHECKED>
 __device__ __forceinline__ double exp_fast_t(double x) {
   const double xc = fmin(fmax(x, -708.0), 709.0);
-  const double t = fma(xc, kExpK[0], kExpK[3]);      // round-to-nearest-integer trick
+  const double t = fma(xc, 1.4426950408889634074, 6755399441055744.0);      // log2(e); 1.5 * 2^52 rounds to nearest integer
   const int n = __double2loint(t);
-  const double fn = t - kExpK[3];
-  double r = fma(fn, kExpK[1], xc);
-  r = fma(fn, kExpK[2], r);
+  const double fn = t - 6755399441055744.0;
+  double r = fma(fn, -6.93147180369123816490e-01, xc);
+  r = fma(fn, -1.90821492927058770002e-10, r);
   // exp(r), |r| <= ln2/2 : Taylor to degree 13 (truncation 4e-18), Estrin evaluation
   const double r2 = r * r;
   const double r4 = r2 * r2;
   const double r8 = r4 * r4;
   const double p01 = 1.0 + r;
-  const double p23 = fma(r, kExpC[3], kExpC[2]);
-  const double p45 = fma(r, kExpC[5], kExpC[4]);
-  const double p67 = fma(r, kExpC[7], kExpC[6]);
-  const double p89 = fma(r, kExpC[9], kExpC[8]);
-  const double pab = fma(r, kExpC[11], kExpC[10]);
-  const double pcd = fma(r, kExpC[13], kExpC[12]);
+  const double p23 = fma(r, (1.0 / 6.0), 0.5);
+  const double p45 = fma(r, (1.0 / 120.0), (1.0 / 24.0));
+  const double p67 = fma(r, (1.0 / 5040.0), (1.0 / 720.0));
+  const double p89 = fma(r, (1.0 / 362880.0), (1.0 / 40320.0));
+  const double pab = fma(r, (1.0 / 39916800.0), (1.0 / 3628800.0));
+  const double pcd = fma(r, (1.0 / 6227020800.0), (1.0 / 479001600.0));
   const double q0 = fma(r2, p23, p01);
   const double q1 = fma(r2, p67, p45);
   const double q2 = fma(r2, pab, p89);
@@ -148,12 +136,12 @@ __device__ __forceinline__ double log_ge1_fast_t(double u) {
   const double s = f * rcp_fast2(2.0 + f);
   const double z = s * s;
   const double w = z * z;
-  const double t1 = w * fma(w, fma(w, kLogC[5], kLogC[3]), kLogC[1]);
-  const double t2 = z * fma(w, fma(w, fma(w, kLogC[6], kLogC[4]), kLogC[2]), kLogC[0]);
+  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
   const double R = t2 + t1;
   const double hfsq = 0.5 * f * f;
   const double dk = (double)k;
-  const double res = fma(dk, kLogC[7], f - (hfsq - fma(s, hfsq + R, dk * kLogC[8])));
+  const double res = fma(dk, 6.93147180369123816490e-01, f - (hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)));
   if (!CHECKED) return res;
   return (u != u) ? u : res;
 }
