@@ -41,7 +41,7 @@ K1, K2 = "exp", "matern52"
 ALPHA, SHIFT, P_CUB = 0.75, 1.0, 9
 EP_ITTS = 20
 # DRAM bytes per time step of the ADF kernel from the committed ncu --set full capture (profiles/); None = not captured
-TRAFFIC_ADF_BYTES_PER_STEP = None
+TRAFFIC_ADF_BYTES_PER_STEP = 6.435328e6 / 20000     # profiles/r1f_full.md (writes were still in L2 when the kernel ended)
 WORKLOAD = ("C2: ihgp_ep_modulator_nmf predict mode, D=16 exp subbands x N=3 matern52 modulators (n=41), "
             "likModulatorPreCalcwn p=9 (S=77), alpha=0.75, ep_itts=20, T=100000, 1 signal per GPU")
 
@@ -332,7 +332,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = 1
-            Tc, ic = 4000, EP_ITTS
+            Tc, ic = 8000, EP_ITTS
             v, per = cpu_arm(1, 0, Tc, ic, cores)
             line["cpu_baseline"] = {"value": v, "unit": "time-steps/s", "cores": cores, "kind": "port",
                                     "sample": "plain-C port of matlab/ihgp_ep_modulator_nmf.m (oracle/c/nsagp_oracle.c, same dense "
