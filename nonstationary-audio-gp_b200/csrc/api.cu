@@ -139,8 +139,9 @@ struct nsagp_plan {
   std::vector<DevState> h_states;
   DevProblem* d_probs = nullptr;
   DevState* d_states = nullptr;
-  double* d_chunk = nullptr;
-  double* d_start = nullptr;
+  double* d_chunk = nullptr;    // scan: one map per (chunk, block)
+  double* d_tile = nullptr;     // scan: one map per (CTA tile, block)
+  double* d_start = nullptr;    // scan: state entering each CTA tile
   double* d_nlZ = nullptr;      // [B][ep_itts + 1]  (last slot: edata)
   double* d_diag = nullptr;     // [B][ep_itts][2]
   double* d_MF = nullptr;       // [B][T][n] filtered means of the last pass (predict mode)
@@ -524,10 +525,13 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
   }
   if ((rc = pl->arena.upload(&pl->d_probs, pl->h_probs)) || (rc = pl->arena.upload(&pl->d_states, pl->h_states)))
     return cleanup(rc);
-  const long long nchunks = (T + kScanChunk - 1) / kScanChunk;
-  const size_t per_chunk = (kind == 0) ? (size_t)(BM * BM + BM) : (size_t)(2 * BM * BM + BM);
-  if ((rc = pl->arena.alloc(&pl->d_chunk, (size_t)B * nchunks * M * per_chunk)) ||
-      (rc = pl->arena.alloc(&pl->d_start, (size_t)B * nchunks * M * (kind == 0 ? BM : BM * BM + BM))) ||
+  const long long nchunks = scan_num_chunks(T);
+  const size_t map_d = (kind == 0) ? (size_t)(BM * BM + BM) : (size_t)(2 * BM * BM + BM);
+  const size_t state_d = (kind == 0) ? (size_t)BM : (size_t)(BM * BM + BM);
+  const long long ntiles_max = scan_num_tiles(T, 1);        // CH >= 1
+  if ((rc = pl->arena.alloc(&pl->d_chunk, (size_t)B * nchunks * M * map_d)) ||
+      (rc = pl->arena.alloc(&pl->d_tile, (size_t)B * ntiles_max * M * map_d)) ||
+      (rc = pl->arena.alloc(&pl->d_start, (size_t)B * ntiles_max * M * state_d)) ||
       (rc = pl->arena.alloc(&pl->d_nlZ, (size_t)B * (pl->ep_itts + 1))) ||
       (rc = pl->arena.alloc(&pl->d_diag, (size_t)B * pl->ep_itts * 2)))
     return cleanup(rc);
@@ -693,22 +697,50 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
   return NSAGP_OK;
 }
 
-template <template <int> class ElemT, int DIR>
-int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int init, long long kinit) {
+// Geometry of the three-phase scan (scan.cuh): CH chunks of kScanSteps steps per CTA tile, limited
+// by the shared memory the tile needs for its chunk aggregates.
+int scan_ch(const nsagp_plan* pl, int map_doubles) {
+  const size_t per_chunk = (size_t)pl->M * map_doubles * sizeof(double);
+  int ch = 16;
+  while (ch > 1 && per_chunk * ch > 96 * 1024) ch >>= 1;
+  return ch;
+}
+
+template <class Elem>
+int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit) {
   if (nsteps <= 0) return NSAGP_OK;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  constexpr int CH = 4;
-  const dim3 block(32, CH);
-  const dim3 grid((unsigned)((nchunks + CH - 1) / CH), pl->B);
-  DISPATCH_BM(pl->BM, {
-    affine_reduce_kernel<BM_, ElemT<BM_>, DIR><<<grid, block, 0, g_stream>>>(pl->d_probs, pl->d_states, kfirst, nsteps, pl->d_chunk);
-    LAUNCH_CHECK();
-    affine_carry_kernel<BM_><<<pl->B, 32, 0, g_stream>>>(pl->d_probs, pl->d_states, nsteps, init, kinit, pl->d_chunk, pl->d_start);
-    LAUNCH_CHECK();
-    affine_apply_kernel<BM_, ElemT<BM_>, DIR><<<grid, block, 0, g_stream>>>(pl->d_probs, pl->d_states, kfirst, nsteps, pl->d_start);
-    LAUNCH_CHECK();
-  });
+  ScanArgs a;
+  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit;
+  a.CH = scan_ch(pl, Elem::kMapDoubles);
+  {
+    // registers: a CTA tile of 32*CH threads must fit the SM's 64 K registers
+    cudaFuncAttributes f1, f3;
+    CU(cudaFuncGetAttributes(&f1, scan_reduce_kernel<Elem>));
+    CU(cudaFuncGetAttributes(&f3, scan_apply_kernel<Elem>));
+    const int regs = std::max(f1.numRegs, f3.numRegs);
+    while (a.CH > 1 && 32 * a.CH * regs > 65536) a.CH >>= 1;
+  }
+  const long long ntiles = scan_num_tiles(nsteps, a.CH);
+  const dim3 block(32, a.CH);
+  const dim3 grid((unsigned)ntiles, pl->B);
+  const size_t sm1 = (size_t)a.CH * pl->M * Elem::kMapDoubles * sizeof(double);
+  const size_t sm3 = (size_t)a.CH * pl->M * Elem::kStateDoubles * sizeof(double);
+  if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  scan_reduce_kernel<Elem><<<grid, block, sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile);
+  LAUNCH_CHECK();
+  scan_carry_kernel<Elem><<<pl->B, 32, 0, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_tile, pl->d_start);
+  LAUNCH_CHECK();
+  scan_apply_kernel<Elem><<<grid, block, sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start);
+  LAUNCH_CHECK();
   return NSAGP_OK;
+}
+
+template <template <int> class ElemT>
+int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit) {
+  int rc = NSAGP_OK;
+  DISPATCH_BM(pl->BM, { rc = run_scan<ElemT<BM_>>(pl, kfirst, nsteps, dir, init, kinit); });
+  return rc;
 }
 
 int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ) {
@@ -743,7 +775,7 @@ int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
       if ((rc = launch_sum(pl, 0, 1))) return rc;
     } else {
       if ((rc = tm.begin(2))) return rc;
-      if ((rc = affine_scan<FilterElem, +1>(pl, 0, T - 1, 0, 0))) return rc;
+      if ((rc = affine_scan<FilterElem>(pl, 0, T - 1, +1, 0, 0))) return rc;
       if ((rc = ihgp_adf(pl, T - 1, T, 0, damp, 0))) return rc;     // last step: moments + update (:253)
       if ((rc = tm.end())) return rc;
     }
@@ -754,7 +786,7 @@ int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
     }
     if (itt < pl->ep_itts) damp = pl->damping[itt];                 // ep_damping(itt+1) (:369-371)
     if ((rc = tm.begin(3))) return rc;
-    if ((rc = affine_scan<SmootherElem, -1>(pl, T - 2, T - 1, 1, T - 1))) return rc;
+    if ((rc = affine_scan<SmootherElem>(pl, T - 2, T - 1, -1, 1, T - 1))) return rc;
     if ((rc = tm.end())) return rc;
     if (itt < pl->ep_itts) {
       if ((rc = tm.begin(4)) || (rc = ihgp_site_update(pl, damp, itt > 1)) || (rc = tm.end())) return rc;

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "mom.cuh"
+#include "scan.cuh"
 
 namespace nsagp {
 
@@ -379,117 +380,73 @@ __device__ __forceinline__ void rts_apply_map(const RtsMap<BM>& e, double (&m)[B
     }
 }
 
-// Processing order s = 0..nsteps-1 maps to time k = T-2-s.
-// Phase 1: compose the chunk's maps.  grid (ceil(nchunks/CH), B), block (32, CH).
+// scan.cuh element of the RTS smoother: processing order s = 0..T-2 is time k = T-2-s.
+// Phase 3 applies the reference's literal step (:229-230), overwrites the stored estimates,
+// emits the marginals and the convergence diagnostics (:231-234, :271-272).
 template <int BM>
-__global__ void rts_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                                  long long T, double* __restrict__ chunk_buf) {
-  const DevProblem& P = probs[blockIdx.y];
-  const DevState& St = states[blockIdx.y];
-  const int n = threadIdx.x;
-  const long long nsteps = T - 1;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  const long long c = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (n >= P.M || c >= nchunks) return;
-  RtsElem<BM> el(P, St, n);
-  RtsStep<BM> st;
-  RtsMap<BM> acc, e;
-  const long long s0 = c * kScanChunk;
-  const long long s1 = (s0 + kScanChunk < nsteps) ? s0 + kScanChunk : nsteps;
-  bool ok = true;
-  el.step(T - 2 - s0, st); ok = ok && st.ok;
-  el.as_map(st, acc);
-  for (long long s = s0 + 1; s < s1; ++s) {
-    el.step(T - 2 - s, st); ok = ok && st.ok;
-    el.as_map(st, e);
-    rts_compose<BM>(acc, e);
-  }
-  if (!ok) atomicCAS(St.status, 0, 1);
-  constexpr int W = 2 * BM * BM + BM;
-  double* dst = chunk_buf + (((size_t)blockIdx.y * nchunks + c) * P.M + n) * W;
-#pragma unroll
-  for (int i = 0; i < BM * BM; ++i) { dst[i] = acc.E[i]; dst[BM * BM + BM + i] = acc.L[i]; }
-#pragma unroll
-  for (int i = 0; i < BM; ++i) dst[BM * BM + i] = acc.g[i];
-}
+struct RtsState {
+  double m[BM], P[BM * BM];
+};
 
-// Phase 2: carry (m, P) across chunks from the filtered estimate at T-1.
 template <int BM>
-__global__ void __launch_bounds__(32)
-rts_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
-                 const double* __restrict__ chunk_buf, double* __restrict__ start_buf) {
-  const DevProblem& P = probs[blockIdx.x];
-  const DevState& St = states[blockIdx.x];
-  const int n = threadIdx.x;
-  if (n >= P.M) return;
-  const long long nsteps = T - 1;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  const int off = P.off[n], b = P.off[n + 1] - off;
-  double m[BM], Pm[BM * BM];
+struct RtsScanElem {
+  using Map = RtsMap<BM>;
+  using State = RtsState<BM>;
+  static constexpr int kMapDoubles = 2 * BM * BM + BM;
+  static constexpr int kStateDoubles = BM * BM + BM;
+  RtsElem<BM> el;
+  bool ok;
+  double mdM, mdP;
+  __device__ RtsScanElem(const DevProblem& P_, const DevState& S_, int n_) : el(P_, S_, n_), ok(true), mdM(0.0), mdP(0.0) {}
+  __device__ static __forceinline__ void compose(Map& acc, const Map& e) { rts_compose<BM>(acc, e); }
+  __device__ static __forceinline__ void apply(const Map& e, State& s) { rts_apply_map<BM>(e, s.m, s.P); }
+  __device__ static __forceinline__ void store_map(const Map& e, double* dst) {
 #pragma unroll
-  for (int i = 0; i < BM; ++i) m[i] = (i < b) ? St.MS[(T - 1) * P.n + off + i] : 0.0;
-  const double* src0 = St.PS + ((size_t)(T - 1) * P.M + n) * BM * BM;
+    for (int i = 0; i < BM * BM; ++i) { dst[i] = e.E[i]; dst[BM * BM + BM + i] = e.L[i]; }
 #pragma unroll
-  for (int i = 0; i < BM * BM; ++i) Pm[i] = src0[i];
-  constexpr int W = 2 * BM * BM + BM;
-  constexpr int SW = BM * BM + BM;
-  for (long long c = 0; c < nchunks; ++c) {
-    const size_t base = (((size_t)blockIdx.x * nchunks + c) * P.M + n);
-    double* st = start_buf + base * SW;
-#pragma unroll
-    for (int i = 0; i < BM; ++i) st[i] = m[i];
-#pragma unroll
-    for (int i = 0; i < BM * BM; ++i) st[BM + i] = Pm[i];
-    const double* src = chunk_buf + base * W;
-    RtsMap<BM> e;
+    for (int i = 0; i < BM; ++i) dst[BM * BM + i] = e.g[i];
+  }
+  __device__ static __forceinline__ void load_map(Map& e, const double* src) {
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) { e.E[i] = src[i]; e.L[i] = src[BM * BM + BM + i]; }
 #pragma unroll
     for (int i = 0; i < BM; ++i) e.g[i] = src[BM * BM + i];
-    rts_apply_map<BM>(e, m, Pm);
   }
-}
-
-// Phase 3: the reference's literal smoother step inside each chunk; overwrite the
-// stored estimates, emit marginals and convergence diagnostics (:229-234,271-272).
-template <int BM>
-__global__ void rts_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                                 long long T, const double* __restrict__ start_buf) {
-  const DevProblem& P = probs[blockIdx.y];
-  const DevState& St = states[blockIdx.y];
-  const int n = threadIdx.x;
-  const long long nsteps = T - 1;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  const long long c = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (n >= P.M || c >= nchunks) return;
-  RtsElem<BM> el(P, St, n);
-  RtsStep<BM> st;
-  constexpr int SW = BM * BM + BM;
-  const double* s0p = start_buf + (((size_t)blockIdx.y * nchunks + c) * P.M + n) * SW;
-  double m[BM], Pm[BM * BM];
+  __device__ static __forceinline__ void store_state(const State& s, double* dst) {
 #pragma unroll
-  for (int i = 0; i < BM; ++i) m[i] = s0p[i];
+    for (int i = 0; i < BM; ++i) dst[i] = s.m[i];
 #pragma unroll
-  for (int i = 0; i < BM * BM; ++i) Pm[i] = s0p[BM + i];
-  const long long s0 = c * kScanChunk;
-  const long long s1 = (s0 + kScanChunk < nsteps) ? s0 + kScanChunk : nsteps;
-  double mdM = 0.0, mdP = 0.0;
-  for (long long s = s0; s < s1; ++s) {
-    const long long k = T - 2 - s;
+    for (int i = 0; i < BM * BM; ++i) dst[BM + i] = s.P[i];
+  }
+  __device__ static __forceinline__ void load_state(State& s, const double* src) {
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.m[i] = src[i];
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) s.P[i] = src[BM + i];
+  }
+  __device__ __forceinline__ void get(long long k, Map& e) {
+    RtsStep<BM> st;
     el.step(k, st);
-    el.apply_step(st, m, Pm);
+    ok = ok && st.ok;
+    el.as_map(st, e);
+  }
+  __device__ __forceinline__ void step(long long k, State& s) {
+    RtsStep<BM> st;
+    el.step(k, st);
+    el.apply_step(st, s.m, s.P);
+    const DevProblem& P = el.P; const DevState& St = el.St; const int n = el.n;
 #pragma unroll
-    for (int i = 0; i < BM; ++i) if (i < el.b) St.MS[k * P.n + el.off + i] = m[i];
+    for (int i = 0; i < BM; ++i) if (i < el.b) St.MS[k * P.n + el.off + i] = s.m[i];
     double* dst = St.PS + ((size_t)k * P.M + n) * BM * BM;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) dst[i] = Pm[i];
+    for (int i = 0; i < BM * BM; ++i) dst[i] = s.P[i];
     double e = 0.0, v = 0.0;
 #pragma unroll
     for (int i = 0; i < BM; ++i) {
-      e = fma(el.hv[i], m[i], e);
+      e = fma(el.hv[i], s.m[i], e);
       double g = 0.0;
 #pragma unroll
-      for (int j = 0; j < BM; ++j) g = fma(el.hv[j], Pm[j + i * BM], g);
+      for (int j = 0; j < BM; ++j) g = fma(el.hv[j], s.P[j + i * BM], g);
       v = fma(g, el.hv[i], v);
     }
     mdM = fmax(mdM, fabs(St.E[k * P.M + n] - e));
@@ -497,8 +454,21 @@ __global__ void rts_apply_kernel(const DevProblem* __restrict__ probs, const Dev
     St.E[k * P.M + n] = e;
     St.V[k * P.M + n] = v;
   }
-  atomic_max_nonneg(St.maxdiff, mdM);
-  atomic_max_nonneg(St.maxdiff + 1, mdP);
-}
+  // the smoother starts from the filtered estimate of the last step, k = kinit = T-1
+  __device__ __forceinline__ void init(State& s, int, long long kinit) {
+    const DevProblem& P = el.P; const DevState& St = el.St;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.m[i] = (i < el.b) ? St.MS[kinit * P.n + el.off + i] : 0.0;
+    const double* src = St.PS + ((size_t)kinit * P.M + el.n) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) s.P[i] = src[i];
+  }
+  __device__ __forceinline__ void store_final(const State&) {}
+  __device__ __forceinline__ void finish_reduce() { if (!ok) atomicCAS(el.St.status, 0, 1); }
+  __device__ __forceinline__ void finish_apply() {
+    atomic_max_nonneg(el.St.maxdiff, mdM);
+    atomic_max_nonneg(el.St.maxdiff + 1, mdP);
+  }
+};
 
 }  // namespace nsagp

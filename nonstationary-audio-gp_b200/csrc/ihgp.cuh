@@ -17,10 +17,10 @@
 #include "common.cuh"
 #include "lookup.cuh"
 #include "mom.cuh"
+#include "scan.cuh"
 
 namespace nsagp {
 
-constexpr int kScanChunk = 128;    // time steps composed by one thread in the scans
 
 __device__ __forceinline__ MomParams make_mom_params(const DevProblem& P, const double* W,
                                                      const double* wn, const double* xn) {
@@ -144,114 +144,50 @@ ihgp_adf_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict
 }
 
 // ------------------------------------------------------ affine scan elements
+// ind = #{i : thr[i] <= R} (thr ascending, nthr entries), trying a 6-entry window around
+// `hint` first: consecutive time steps have similar R, and one round trip to L1 replaces the
+// eight dependent ones of a binary search.
+__device__ __forceinline__ int count_le_window(const double* __restrict__ thr, int nthr, double R, int hint) {
+  const int last = nthr - 1;
+  const int h = min(max(hint, 0), last);
+  const int lo = max(h - 3, 0), hi = min(h + 2, last);
+  int cnt = 0;
+  bool first = false, end = false;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int i = min(lo + j, hi);
+    const bool le = thr[i] <= R;
+    cnt += (lo + j <= hi && le) ? 1 : 0;
+    if (j == 0) first = le;
+    end = le;
+  }
+  if ((lo == 0 || first) && (hi == last || !end)) return lo + cnt;
+  return nearest_by_threshold(thr, nthr + 1, R);
+}
+
+__device__ __forceinline__ int lookup_filter_hint(const double* r, const double* thr, int nr, double R, int hint) {
+  if (!(R > 0.0)) return 0;
+  if (isinf(R)) return 0;
+  if (R >= kLookupBig) return nearest_bruteforce(r, nr, R);
+  return count_le_window(thr, nr - 1, R, hint);
+}
+
+__device__ __forceinline__ int lookup_smoother_hint(const double* r, const double* thr, int nr, double R, int hint) {
+  if (isinf(R)) return nr - 1;
+  if (!(R > 0.0)) return 0;
+  if (R >= kLookupBig) return nearest_bruteforce(r, nr, R);
+  return count_le_window(thr, nr - 1, R, hint);
+}
+
 template <int BM>
 struct Affine {
   double F[BM * BM];     // column-major
   double c[BM];
 };
 
-// Frozen-site filter step k as an affine map of the block mean (:280-304).
 template <int BM>
-struct FilterElem {
-  const DevProblem& P; const DevState& St; int n;
-  double A[BM * BM], hA[BM];
-  __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_) {
-#pragma unroll
-    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
-#pragma unroll
-    for (int i = 0; i < BM; ++i) hA[i] = P.hA[n * BM + i];
-  }
-  // writes back the clamp / Inf marking of the reference's filter loop when `commit`
-  __device__ __forceinline__ void get(long long k, Affine<BM>& e, bool commit) const {
-    const int M = P.M, nr = P.nr;
-    const double tt = fmax(St.ttau[k * M + n], 0.0);                          // :274
-    if (tt == 0.0) {
-#pragma unroll
-      for (int i = 0; i < BM * BM; ++i) e.F[i] = A[i];
-#pragma unroll
-      for (int i = 0; i < BM; ++i) e.c[i] = 0.0;
-      if (commit) { St.ttau[k * M + n] = 0.0; St.R[k * M + n] = INFINITY; }
-      return;
-    }
-    int idx = nr;
-    if (k > 0) {
-      const double ttp = fmax(St.ttau[(k - 1) * M + n], 0.0);
-      const double Rp = (ttp == 0.0) ? INFINITY : St.R[(k - 1) * M + n];
-      idx = lookup_filter(P.r, P.thr, nr, Rp);
-    }
-    const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BM;
-    const double HPH = P.HPHtab[(size_t)n * (nr + 1) + idx];
-    const double g = 1.0 / (HPH + St.R[k * M + n]);
-    const double ys = St.tnu[k * M + n] / tt;
-#pragma unroll
-    for (int i = 0; i < BM; ++i) {
-      const double Ki = wrow[i] * g;
-      e.c[i] = Ki * ys;
-#pragma unroll
-      for (int j = 0; j < BM; ++j) e.F[i + j * BM] = fma(-Ki, hA[j], A[i + j * BM]);   // A - K (h A)
-    }
-  }
-  __device__ __forceinline__ void emit(long long k, const double (&m)[BM]) const {
-    const int off = P.off[n], b = P.off[n + 1] - off;
-#pragma unroll
-    for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P.n + off + i] = m[i];
-  }
-};
-
-// RTS mean step k (:379-394): m_k = MS_k + G_k (m_{k+1} - A MS_k).
-template <int BM>
-struct SmootherElem {
-  const DevProblem& P; const DevState& St; int n;
-  double A[BM * BM], hv[BM];
-  __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_) {
-#pragma unroll
-    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
-#pragma unroll
-    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BM + i];
-  }
-  __device__ __forceinline__ void get(long long k, Affine<BM>& e, bool commit) const {
-    const int M = P.M, nr = P.nr;
-    const int off = P.off[n], b = P.off[n + 1] - off;
-    const int idx = lookup_smoother(P.r, P.thr, nr, St.R[k * M + n]);
-    const double* G = P.Gtab + ((size_t)n * nr + idx) * BM * BM;
-    double ms[BM], t[BM];
-#pragma unroll
-    for (int i = 0; i < BM; ++i) ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
-#pragma unroll
-    for (int i = 0; i < BM; ++i) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < BM; ++j) acc = fma(A[i + j * BM], ms[j], acc);
-      t[i] = acc;
-    }
-#pragma unroll
-    for (int i = 0; i < BM * BM; ++i) e.F[i] = G[i];
-#pragma unroll
-    for (int i = 0; i < BM; ++i) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < BM; ++j) acc = fma(e.F[i + j * BM], t[j], acc);
-      e.c[i] = ms[i] - acc;
-    }
-    if (commit && k == 0) {
-      // marginal variance of the last look-up: the reference's Varft (:492) and maxDiffP (:444)
-      const double vm = P.vmtab[(size_t)n * nr + idx];
-      atomic_max_nonneg(St.maxdiff + 1, fabs(St.vm0[n] - vm));
-      St.vm0[n] = vm;
-    }
-  }
-  __device__ __forceinline__ void emit(long long k, const double (&m)[BM]) const {
-    const int off = P.off[n], b = P.off[n + 1] - off;
-    double e = 0.0;
-#pragma unroll
-    for (int i = 0; i < BM; ++i) {
-      if (i < b) St.MS[k * P.n + off + i] = m[i];
-      e = fma(hv[i], m[i], e);
-    }
-    // maxDiffM (:440): against H*MS of the previous iteration's smoother
-    atomic_max_nonneg(St.maxdiff, fabs(St.E[k * P.M + n] - e));
-    St.E[k * P.M + n] = e;
-  }
+struct MeanState {
+  double m[BM];
 };
 
 template <int BM>
@@ -292,94 +228,168 @@ __device__ __forceinline__ void affine_apply(const Affine<BM>& e, double (&m)[BM
   for (int i = 0; i < BM; ++i) m[i] = r[i];
 }
 
-// Steps are numbered 0..nsteps-1 in PROCESSING order; step s maps to time
-// k = kfirst + s (forward) or kfirst - s (backward).
-// Phase 1: one thread per (chunk, block) composes its chunk's affine maps.
-// grid = (ceil(nchunks / blockDim.y), B), block = (32, CH).
-template <int BM, class Elem, int DIR>
-__global__ void affine_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                                     long long kfirst, long long nsteps, double* __restrict__ chunk_buf) {
-  const DevProblem& P = probs[blockIdx.y];
-  const DevState& St = states[blockIdx.y];
-  const int n = threadIdx.x;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  const long long c = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (n >= P.M || c >= nchunks) return;
-  Elem el(P, St, n);
-  Affine<BM> acc, e;
-  const long long s0 = c * kScanChunk;
-  const long long s1 = (s0 + kScanChunk < nsteps) ? s0 + kScanChunk : nsteps;
-  el.get(kfirst + DIR * s0, acc, false);
-  for (long long s = s0 + 1; s < s1; ++s) {
-    el.get(kfirst + DIR * s, e, false);
-    affine_compose<BM>(acc, e);
-  }
-  constexpr int W = BM * BM + BM;
-  double* dst = chunk_buf + (((size_t)blockIdx.y * nchunks + c) * P.M + n) * W;
-#pragma unroll
-  for (int i = 0; i < BM * BM; ++i) dst[i] = acc.F[i];
-#pragma unroll
-  for (int i = 0; i < BM; ++i) dst[BM * BM + i] = acc.c[i];
-}
-
-// Phase 2: one warp per signal walks the chunk aggregates, recording the state
-// entering each chunk.  init: 0 = St.mcarry (filter), 1 = MS[kinit] (smoother).
+// What the two IHGP mean recursions share (scan.cuh's Elem interface).
 template <int BM>
-__global__ void __launch_bounds__(32)
-affine_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                    long long nsteps, int init, long long kinit, const double* __restrict__ chunk_buf,
-                    double* __restrict__ start_buf) {
-  const DevProblem& P = probs[blockIdx.x];
-  const DevState& St = states[blockIdx.x];
-  const int n = threadIdx.x;
-  if (n >= P.M) return;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  const int off = P.off[n], b = P.off[n + 1] - off;
-  double m[BM];
+struct AffineElemBase {
+  using Map = Affine<BM>;
+  using State = MeanState<BM>;
+  static constexpr int kMapDoubles = BM * BM + BM;
+  static constexpr int kStateDoubles = BM;
+  __device__ static __forceinline__ void compose(Map& acc, const Map& e) { affine_compose<BM>(acc, e); }
+  __device__ static __forceinline__ void apply(const Map& e, State& s) { affine_apply<BM>(e, s.m); }
+  __device__ static __forceinline__ void store_map(const Map& e, double* dst) {
 #pragma unroll
-  for (int i = 0; i < BM; ++i)
-    m[i] = init ? ((i < b) ? St.MS[kinit * P.n + off + i] : 0.0) : St.mcarry[n * BM + i];
-  constexpr int W = BM * BM + BM;
-  for (long long c = 0; c < nchunks; ++c) {
-    const size_t base = (((size_t)blockIdx.x * nchunks + c) * P.M + n);
-    double* st = start_buf + base * BM;
+    for (int i = 0; i < BM * BM; ++i) dst[i] = e.F[i];
 #pragma unroll
-    for (int i = 0; i < BM; ++i) st[i] = m[i];
-    const double* src = chunk_buf + base * W;
-    Affine<BM> e;
+    for (int i = 0; i < BM; ++i) dst[BM * BM + i] = e.c[i];
+  }
+  __device__ static __forceinline__ void load_map(Map& e, const double* src) {
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) e.F[i] = src[i];
 #pragma unroll
     for (int i = 0; i < BM; ++i) e.c[i] = src[BM * BM + i];
-    affine_apply<BM>(e, m);
   }
-}
-
-// Phase 3: re-apply the maps inside each chunk from its entering state and emit.
-template <int BM, class Elem, int DIR>
-__global__ void affine_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                                    long long kfirst, long long nsteps, const double* __restrict__ start_buf) {
-  const DevProblem& P = probs[blockIdx.y];
-  const DevState& St = states[blockIdx.y];
-  const int n = threadIdx.x;
-  const long long nchunks = (nsteps + kScanChunk - 1) / kScanChunk;
-  const long long c = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (n >= P.M || c >= nchunks) return;
-  Elem el(P, St, n);
-  double m[BM];
-  const double* st = start_buf + (((size_t)blockIdx.y * nchunks + c) * P.M + n) * BM;
+  __device__ static __forceinline__ void store_state(const State& s, double* dst) {
 #pragma unroll
-  for (int i = 0; i < BM; ++i) m[i] = st[i];
-  Affine<BM> e;
-  const long long s0 = c * kScanChunk;
-  const long long s1 = (s0 + kScanChunk < nsteps) ? s0 + kScanChunk : nsteps;
-  for (long long s = s0; s < s1; ++s) {
-    const long long k = kfirst + DIR * s;
-    el.get(k, e, true);
-    affine_apply<BM>(e, m);
-    el.emit(k, m);
+    for (int i = 0; i < BM; ++i) dst[i] = s.m[i];
   }
-}
+  __device__ static __forceinline__ void load_state(State& s, const double* src) {
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.m[i] = src[i];
+  }
+};
+
+// Frozen-site filter step k as an affine map of the block mean (:280-304).
+template <int BM>
+struct FilterElem : AffineElemBase<BM> {
+  using Map = Affine<BM>;
+  using State = MeanState<BM>;
+  const DevProblem& P; const DevState& St; int n, off, b, hint;
+  double A[BM * BM], hA[BM];
+  __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_), hint(0) {
+    off = P.off[n]; b = P.off[n + 1] - off;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) hA[i] = P.hA[n * BM + i];
+  }
+  // commit: write back the clamp / Inf marking of the reference's filter loop (:274,:287)
+  __device__ __forceinline__ void get_impl(long long k, Map& e, bool commit) {
+    const int M = P.M, nr = P.nr;
+    const double tt = fmax(St.ttau[k * M + n], 0.0);                          // :274
+    if (tt == 0.0) {
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) e.F[i] = A[i];
+#pragma unroll
+      for (int i = 0; i < BM; ++i) e.c[i] = 0.0;
+      if (commit) { St.ttau[k * M + n] = 0.0; St.R[k * M + n] = INFINITY; }
+      return;
+    }
+    int idx = nr;
+    if (k > 0) {
+      const double ttp = fmax(St.ttau[(k - 1) * M + n], 0.0);
+      const double Rp = (ttp == 0.0) ? INFINITY : St.R[(k - 1) * M + n];
+      idx = lookup_filter_hint(P.r, P.thr, nr, Rp, hint);
+      hint = idx;
+    }
+    const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BM;
+    const double HPH = P.HPHtab[(size_t)n * (nr + 1) + idx];
+    const double g = 1.0 / (HPH + St.R[k * M + n]);
+    const double ys = St.tnu[k * M + n] / tt;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      const double Ki = wrow[i] * g;
+      e.c[i] = Ki * ys;
+#pragma unroll
+      for (int j = 0; j < BM; ++j) e.F[i + j * BM] = fma(-Ki, hA[j], A[i + j * BM]);   // A - K (h A)
+    }
+  }
+  __device__ __forceinline__ void get(long long k, Map& e) { get_impl(k, e, false); }
+  __device__ __forceinline__ void step(long long k, State& s) {
+    Map e;
+    get_impl(k, e, true);
+    affine_apply<BM>(e, s.m);
+#pragma unroll
+    for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P.n + off + i] = s.m[i];
+  }
+  __device__ __forceinline__ void init(State& s, int, long long) {            // m carried from the previous smoother pass
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.m[i] = St.mcarry[n * BM + i];
+  }
+  __device__ __forceinline__ void store_final(const State&) {}
+  __device__ __forceinline__ void finish_reduce() {}
+  __device__ __forceinline__ void finish_apply() {}
+};
+
+// RTS mean step k (:379-394): m_k = MS_k + G_k (m_{k+1} - A MS_k).
+template <int BM>
+struct SmootherElem : AffineElemBase<BM> {
+  using Map = Affine<BM>;
+  using State = MeanState<BM>;
+  const DevProblem& P; const DevState& St; int n, off, b, hint;
+  double A[BM * BM], hv[BM];
+  double mdM;
+  __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_), hint(0), mdM(0.0) {
+    off = P.off[n]; b = P.off[n + 1] - off;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BM + i];
+  }
+  __device__ __forceinline__ void get_impl(long long k, Map& e, bool commit) {
+    const int M = P.M, nr = P.nr;
+    const int idx = lookup_smoother_hint(P.r, P.thr, nr, St.R[k * M + n], hint);
+    hint = idx;
+    const double* G = P.Gtab + ((size_t)n * nr + idx) * BM * BM;
+    double ms[BM], t[BM];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < BM; ++j) acc = fma(A[i + j * BM], ms[j], acc);
+      t[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) e.F[i] = G[i];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < BM; ++j) acc = fma(e.F[i + j * BM], t[j], acc);
+      e.c[i] = ms[i] - acc;
+    }
+    if (commit && k == 0) {
+      // marginal variance of the last look-up: the reference's Varft (:492) and maxDiffP (:444)
+      const double vm = P.vmtab[(size_t)n * nr + idx];
+      atomic_max_nonneg(St.maxdiff + 1, fabs(St.vm0[n] - vm));
+      St.vm0[n] = vm;
+    }
+  }
+  __device__ __forceinline__ void get(long long k, Map& e) { get_impl(k, e, false); }
+  __device__ __forceinline__ void step(long long k, State& s) {
+    Map e;
+    get_impl(k, e, true);
+    affine_apply<BM>(e, s.m);
+    double ev = 0.0;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      if (i < b) St.MS[k * P.n + off + i] = s.m[i];
+      ev = fma(hv[i], s.m[i], ev);
+    }
+    // maxDiffM (:440): against H*MS of the previous iteration's smoother
+    mdM = fmax(mdM, fabs(St.E[k * P.M + n] - ev));
+    St.E[k * P.M + n] = ev;
+  }
+  __device__ __forceinline__ void init(State& s, int, long long kinit) {      // m starts at the filtered mean of the last step
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.m[i] = (i < b) ? St.MS[kinit * P.n + off + i] : 0.0;
+  }
+  __device__ __forceinline__ void store_final(const State&) {}
+  __device__ __forceinline__ void finish_reduce() {}
+  __device__ __forceinline__ void finish_apply() { atomic_max_nonneg(St.maxdiff, mdM); }
+};
 
 // -------------------------------------------------------- site update (EP)
 // One thread per time step k in [0, T-1): cavity from the smoothed marginal,

@@ -1,0 +1,161 @@
+// Three-phase chunked scan over time for the passes that are linear once the EP sites
+// are frozen (every IHGP filter pass >= 2, every RTS smoother pass).
+//
+// An element type `Elem` describes one block's recursion:
+//   Map   : the associative element of one step (affine map of the mean; (E, g, L) of the
+//           RTS smoother, Sarkka & Garcia-Fernandez 2021), with compose / apply;
+//   State : what is carried (mean, or mean + covariance);
+//   step  : the reference's LITERAL step applied to a State, emitting the outputs.
+// Steps are numbered 0..nsteps-1 in PROCESSING order; step s is time k = kfirst + dir*s.
+//
+//   phase 1  scan_reduce : thread (block n, chunk c) composes the kSteps maps of its chunk; the
+//            CTA's chunks are then composed in order by warp 0 (from shared memory) into one
+//            CTA aggregate.  Chunk aggregates and CTA aggregates go to HBM.
+//   phase 2  scan_carry  : one warp per signal walks the CTA aggregates (prefetched ahead),
+//            recording the state entering every CTA tile.  This is the only sequential part:
+//            nsteps / (kSteps * CH) applications -- and the only part that would cross GPUs
+//            when a signal is time-chunked over ranks (the carry exchange).
+//   phase 3  scan_apply  : warp 0 turns the entering state + chunk aggregates into the state
+//            entering every chunk (shared memory); every thread then re-applies the literal
+//            steps of its chunk and emits.  Only the chunk-entry states are re-associated.
+//
+// Thread layout: threadIdx.x = latent block n (coalesced M-contiguous site loads, 32 lanes),
+// threadIdx.y = chunk within the CTA tile (CH chunks), grid = (tiles, signals).
+#pragma once
+#include "common.cuh"
+
+namespace nsagp {
+
+constexpr int kScanSteps = 32;     // time steps composed by one thread
+
+struct ScanArgs {
+  long long kfirst, nsteps;
+  int dir;                         // +1 forward in time, -1 backward
+  int init;                        // Elem-specific initial-state selector
+  long long kinit;
+  int CH;                          // chunks per CTA tile (blockDim.y)
+};
+
+__host__ __device__ inline long long scan_num_chunks(long long nsteps) { return (nsteps + kScanSteps - 1) / kScanSteps; }
+__host__ __device__ inline long long scan_num_tiles(long long nsteps, int CH) {
+  const long long per = (long long)kScanSteps * CH;
+  return (nsteps + per - 1) / per;
+}
+
+template <class Elem>
+__global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                                   ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf) {
+  using Map = typename Elem::Map;
+  constexpr int W = Elem::kMapDoubles;
+  const DevProblem& P = probs[blockIdx.y];
+  const DevState& St = states[blockIdx.y];
+  const int n = threadIdx.x, c = threadIdx.y, M = P.M, CH = a.CH;
+  extern __shared__ double sm[];                 // [CH][M][W]
+  const long long nchunks = scan_num_chunks(a.nsteps);
+  const long long ntiles = scan_num_tiles(a.nsteps, CH);
+  const long long chunk = (long long)blockIdx.x * CH + c;
+  const bool live = n < M && chunk < nchunks;
+  if (n < M) {
+    Map acc;
+    if (live) {
+      Elem el(P, St, n);
+      Map e;
+      const long long s0 = chunk * kScanSteps;
+      const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
+      el.get(a.kfirst + a.dir * s0, acc);
+      for (long long s = s0 + 1; s < s1; ++s) {
+        el.get(a.kfirst + a.dir * s, e);
+        Elem::compose(acc, e);
+      }
+      el.finish_reduce();
+      Elem::store_map(acc, chunk_buf + (((size_t)blockIdx.y * nchunks + chunk) * M + n) * W);
+      Elem::store_map(acc, sm + ((size_t)c * M + n) * W);
+    }
+  }
+  __syncthreads();
+  if (c == 0 && n < M) {
+    // compose this tile's chunks in processing order
+    const long long first = (long long)blockIdx.x * CH;
+    const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
+    Map acc, e;
+    Elem::load_map(acc, sm + (size_t)n * W);
+    for (int j = 1; j < cnt; ++j) {
+      Elem::load_map(e, sm + ((size_t)j * M + n) * W);
+      Elem::compose(acc, e);
+    }
+    Elem::store_map(acc, tile_buf + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * W);
+  }
+}
+
+// One warp per signal.  tile_start[(b, tile, n)] = state entering the tile.
+template <class Elem>
+__global__ void __launch_bounds__(32)
+scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, ScanArgs a,
+                  const double* __restrict__ tile_buf, double* __restrict__ tile_start) {
+  using Map = typename Elem::Map;
+  using State = typename Elem::State;
+  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
+  const DevProblem& P = probs[blockIdx.x];
+  const DevState& St = states[blockIdx.x];
+  const int n = threadIdx.x, M = P.M;
+  if (n >= M) return;
+  const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
+  Elem el(P, St, n);
+  State s;
+  el.init(s, a.init, a.kinit);
+  const double* src = tile_buf + ((size_t)blockIdx.x * ntiles * M + n) * W;
+  double* dst = tile_start + ((size_t)blockIdx.x * ntiles * M + n) * SW;
+  const size_t stride = (size_t)M * W, dstride = (size_t)M * SW;
+  // the walk is latency bound: keep the next aggregates in flight
+  Map cur, nxt;
+  Elem::load_map(cur, src);
+  for (long long t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) Elem::load_map(nxt, src + (size_t)(t + 1) * stride);
+    Elem::store_state(s, dst + (size_t)t * dstride);
+    Elem::apply(cur, s);
+    cur = nxt;
+  }
+  el.store_final(s);               // the state after the last step (used by a following tile / rank)
+}
+
+template <class Elem>
+__global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                                  ScanArgs a, const double* __restrict__ chunk_buf,
+                                  const double* __restrict__ tile_start) {
+  using Map = typename Elem::Map;
+  using State = typename Elem::State;
+  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
+  const DevProblem& P = probs[blockIdx.y];
+  const DevState& St = states[blockIdx.y];
+  const int n = threadIdx.x, c = threadIdx.y, M = P.M, CH = a.CH;
+  extern __shared__ double sm[];                 // [CH][M][SW] states entering each chunk
+  const long long nchunks = scan_num_chunks(a.nsteps);
+  const long long ntiles = scan_num_tiles(a.nsteps, CH);
+  const long long first = (long long)blockIdx.x * CH;
+  if (c == 0 && n < M) {
+    const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
+    State s;
+    Elem::load_state(s, tile_start + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * SW);
+    const double* src = chunk_buf + (((size_t)blockIdx.y * nchunks + first) * M + n) * W;
+    Map cur, nxt;
+    Elem::load_map(cur, src);
+    for (int j = 0; j < cnt; ++j) {
+      if (j + 1 < cnt) Elem::load_map(nxt, src + (size_t)(j + 1) * M * W);
+      Elem::store_state(s, sm + ((size_t)j * M + n) * SW);
+      Elem::apply(cur, s);
+      cur = nxt;
+    }
+  }
+  __syncthreads();
+  const long long chunk = first + c;
+  if (n >= M || chunk >= nchunks) return;
+  Elem el(P, St, n);
+  State s;
+  Elem::load_state(s, sm + ((size_t)c * M + n) * SW);
+  const long long s0 = chunk * kScanSteps;
+  const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
+  for (long long t = s0; t < s1; ++t) el.step(a.kfirst + a.dir * t, s);
+  el.finish_apply();
+}
+
+}  // namespace nsagp
