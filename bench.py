@@ -187,6 +187,8 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     lib_mod.check(L.nsagp_set_device(local_rank))
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "ERROR"          # keep stdout to the one JSON line (NCCL prints its version there)
     dist = None
     if world > 1:
         import torch.distributed as dist

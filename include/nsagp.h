@@ -126,6 +126,10 @@ int nsagp_set_device(int device);
 int nsagp_set_stream(void* cuda_stream);
 int nsagp_device_count(void);
 
+/* Device buffers of finished calls are kept for the next call of the same shapes (the entry
+ * points are called thousands of times by fminunc); this returns them to the driver. */
+int nsagp_release_cache(void);
+
 /* Number of kernel launches issued by this library since the last reset
  * (bench.py reports it as gpu_launches). */
 int64_t nsagp_launch_count(int reset);

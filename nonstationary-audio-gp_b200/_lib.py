@@ -118,7 +118,7 @@ EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_s
            "nsagp_launch_count", "nsagp_mom_batch", "nsagp_mom_batch_warp", "nsagp_ep_ihgp", "nsagp_ep_full",
            "nsagp_ep_ihgp_batch", "nsagp_ep_full_batch", "nsagp_plan_create", "nsagp_plan_run",
            "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings", "nsagp_plan_keep_pf",
-           "nsagp_plan_set_adf_form", "nsagp_fastmath_eval"]
+           "nsagp_plan_set_adf_form", "nsagp_fastmath_eval", "nsagp_release_cache"]
 
 
 def check(status):

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -98,16 +99,52 @@ double bisect_ttau_threshold(double thr) {
   return x;
 }
 
+// Device memory cache.  The entry points are called thousands of times with the same shapes
+// (fminunc around the nlZ mode, demo_toy_modulators_nmf.m:100-104), and cudaMalloc / cudaFree
+// cost more than a short EP run, so released blocks are kept (per host thread, exact-size bins
+// rounded up to 256 B) and handed out again.  nsagp_release_cache() returns them to the driver.
+struct DeviceCache {
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = (size_t)64 << 30;
+  void* take(size_t nb) {
+    auto it = free_blocks.find(nb);
+    if (it == free_blocks.end()) return nullptr;
+    void* q = it->second;
+    free_blocks.erase(it);
+    cached_bytes -= nb;
+    return q;
+  }
+  void give(void* q, size_t nb) {
+    if (cached_bytes + nb > kMaxCached) { cudaFree(q); return; }
+    free_blocks.emplace(nb, q);
+    cached_bytes += nb;
+  }
+  void clear() {
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+thread_local DeviceCache g_cache;
+
 struct DeviceArena {
-  std::vector<void*> ptrs;
+  std::vector<std::pair<void*, size_t>> ptrs;
   size_t bytes = 0;
   template <class T>
   int alloc(T** p, size_t count) {
-    void* q = nullptr;
-    const size_t nb = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(&q, nb);
-    if (e != cudaSuccess) return fail(NSAGP_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    ptrs.push_back(q);
+    const size_t nb = ((std::max<size_t>(count, 1) * sizeof(T)) + 255) & ~(size_t)255;
+    void* q = g_cache.take(nb);
+    if (!q) {
+      cudaError_t e = cudaMalloc(&q, nb);
+      if (e != cudaSuccess) {                       // out of memory: give the cache back and retry once
+        cudaGetLastError();
+        g_cache.clear();
+        e = cudaMalloc(&q, nb);
+      }
+      if (e != cudaSuccess) return fail(NSAGP_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    ptrs.emplace_back(q, nb);
     bytes += nb;
     *p = static_cast<T*>(q);
     return NSAGP_OK;
@@ -120,7 +157,7 @@ struct DeviceArena {
     return NSAGP_OK;
   }
   void release() {
-    for (void* q : ptrs) cudaFree(q);
+    for (auto& q : ptrs) g_cache.give(q.first, q.second);
     ptrs.clear();
   }
 };
@@ -147,6 +184,7 @@ struct nsagp_plan {
   double* d_MF = nullptr;       // [B][T][n] filtered means of the last pass (predict mode)
   double* d_PF = nullptr;       // [B][T][PB] filtered covariances of the last pass (full-state, predict)
   double* d_y = nullptr;
+  double* d_bounds = nullptr;   // [3][T][M] Varft / lb / ub staging for fetch
   std::vector<double> h_vminf;  // [B][M] h Pinf h'
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> phase_ev;
@@ -552,6 +590,11 @@ int nsagp_plan_keep_pf(nsagp_plan* pl, int keep) {
   return NSAGP_OK;
 }
 
+int nsagp_release_cache(void) {
+  g_cache.clear();
+  return NSAGP_OK;
+}
+
 int nsagp_plan_set_adf_form(nsagp_plan* pl, int form) {
   if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
   if (form != 0 && form != 1) return fail(NSAGP_ERR_INVALID, "adf form must be 0 (CTA per signal) or 1 (warp per signal)");
@@ -573,6 +616,20 @@ int nsagp_plan_destroy(nsagp_plan* pl) {
 
 // ------------------------------------------------------------ run: dispatch
 namespace {
+
+// lb/ub = Eft -/+ 1.96 sqrt(Varft) (gf_ep_modulator_nmf.m:346-347).  IHGP: Varft is one M-vector
+// (marginal variance of the last look-up) replicated over time with abs() (ihgp_ep_modulator_nmf.m:492-496).
+__global__ void bounds_kernel(const double* __restrict__ E, const double* __restrict__ V, const double* __restrict__ vm0,
+                              int M, long long total, double* __restrict__ Vout, double* __restrict__ lb,
+                              double* __restrict__ ub) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double v = vm0 ? fabs(vm0[i % M]) : V[i];
+  const double sd = 1.96 * sqrt(v);
+  if (Vout) Vout[i] = v;
+  if (lb) lb[i] = E[i] - sd;
+  if (ub) ub[i] = E[i] + sd;
+}
 
 // (variadic: the bodies contain commas, e.g. in <<<...>>>)
 #define DISPATCH_BM(BMV, ...)                                             \
@@ -702,7 +759,7 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
 int scan_ch(const nsagp_plan* pl, int map_doubles) {
   const size_t per_chunk = (size_t)pl->M * map_doubles * sizeof(double);
   int ch = 16;
-  while (ch > 1 && per_chunk * ch > 96 * 1024) ch >>= 1;
+  while (ch > 1 && per_chunk * ch > 80 * 1024) ch >>= 1;     // phase 3 stages maps + states: < 2x this
   return ch;
 }
 
@@ -724,13 +781,19 @@ int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int in
   const dim3 block(32, a.CH);
   const dim3 grid((unsigned)ntiles, pl->B);
   const size_t sm1 = (size_t)a.CH * pl->M * Elem::kMapDoubles * sizeof(double);
-  const size_t sm3 = (size_t)a.CH * pl->M * Elem::kStateDoubles * sizeof(double);
+  const size_t sm3 = (size_t)a.CH * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
   if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
   if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   scan_reduce_kernel<Elem><<<grid, block, sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile);
   LAUNCH_CHECK();
-  scan_carry_kernel<Elem><<<pl->B, 32, 0, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_tile, pl->d_start);
-  LAUNCH_CHECK();
+  {
+    const size_t per_tile = (size_t)pl->M * Elem::kMapDoubles * sizeof(double);
+    int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)ntiles, (64 * 1024) / per_tile));
+    const size_t sm2 = per_tile * batch;
+    if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(scan_carry_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    scan_carry_kernel<Elem><<<pl->B, kCarryThreads, sm2, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_tile, pl->d_start, batch);
+    LAUNCH_CHECK();
+  }
   scan_apply_kernel<Elem><<<grid, block, sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start);
   LAUNCH_CHECK();
   return NSAGP_OK;
@@ -896,41 +959,23 @@ int nsagp_plan_fetch(nsagp_plan* pl, int32_t b, nsagp_outputs* o) {
   }
   unsigned long long neg = 0;
   if (o->n_negcav) CU(cudaMemcpyAsync(&neg, St.negcav, 8, cudaMemcpyDeviceToHost, g_stream));
-  std::vector<double> vm0;
-  if (predict && pl->kind == 0 && (o->Varft || o->lb || o->ub)) {
-    vm0.resize(M);
-    CU(cudaMemcpyAsync(vm0.data(), St.vm0, M * 8, cudaMemcpyDeviceToHost, g_stream));
+  if (predict && ((pl->kind == 0 && o->Varft) || o->lb || o->ub)) {
+    const long long total = (long long)T * M;
+    if (!pl->d_bounds) { int rc2 = pl->arena.alloc(&pl->d_bounds, (size_t)3 * total); if (rc2) return rc2; }
+    double* dV = pl->d_bounds; double* dlb = dV + total; double* dub = dlb + total;
+    bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, g_stream>>>(St.E, St.V, pl->kind == 0 ? St.vm0 : nullptr, M, total,
+                                                                        pl->kind == 0 ? dV : nullptr, o->lb ? dlb : nullptr,
+                                                                        o->ub ? dub : nullptr);
+    LAUNCH_CHECK();
+    if (pl->kind == 0 && o->Varft) CU(cudaMemcpyAsync(o->Varft, dV, TM, cudaMemcpyDeviceToHost, g_stream));
+    if (o->lb) CU(cudaMemcpyAsync(o->lb, dlb, TM, cudaMemcpyDeviceToHost, g_stream));
+    if (o->ub) CU(cudaMemcpyAsync(o->ub, dub, TM, cudaMemcpyDeviceToHost, g_stream));
   }
   CU(cudaStreamSynchronize(g_stream));
   if (o->n_negcav) *o->n_negcav = (int64_t)neg;
   for (int i = 0; i < pl->ep_itts && !diag.empty(); ++i) {
     if (o->maxDiffM) o->maxDiffM[i] = diag[2 * i];
     if (o->maxDiffP) o->maxDiffP[i] = diag[2 * i + 1];
-  }
-  if (predict && pl->kind == 0) {
-    // Varft: one M-vector (marginal variance of the last look-up) replicated over
-    // time, abs() as in ihgp_ep_modulator_nmf.m:492-496
-    if (o->Varft)
-      for (long long k = 0; k < T; ++k)
-        for (int i = 0; i < M; ++i) o->Varft[k * M + i] = std::fabs(vm0[i]);
-  }
-  if (predict && (o->lb || o->ub)) {
-    // lb/ub = Eft -/+ 1.96 sqrt(Varft)  (gf_ep_modulator_nmf.m:346-347)
-    std::vector<double> Etmp, Vtmp;
-    const double* E = o->Eft;
-    const double* V = o->Varft;
-    if (!E) { Etmp.resize((size_t)T * M); CU(cudaMemcpy(Etmp.data(), St.E, TM, cudaMemcpyDeviceToHost)); E = Etmp.data(); }
-    if (!V) {
-      Vtmp.resize((size_t)T * M);
-      if (pl->kind == 0) { for (long long k = 0; k < T; ++k) for (int i = 0; i < M; ++i) Vtmp[k * M + i] = std::fabs(vm0[i]); }
-      else CU(cudaMemcpy(Vtmp.data(), St.V, TM, cudaMemcpyDeviceToHost));
-      V = Vtmp.data();
-    }
-    for (size_t i = 0; i < (size_t)T * M; ++i) {
-      const double sd = 1.96 * std::sqrt(V[i]);
-      if (o->lb) o->lb[i] = E[i] - sd;
-      if (o->ub) o->ub[i] = E[i] + sd;
-    }
   }
   return NSAGP_OK;
 }

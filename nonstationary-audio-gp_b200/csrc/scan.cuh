@@ -87,35 +87,45 @@ __global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const D
   }
 }
 
-// One warp per signal.  tile_start[(b, tile, n)] = state entering the tile.
+// One CTA per signal.  tile_start[(b, tile, n)] = state entering the tile.  The walk over the
+// tile aggregates is the sequential part of the scan, so its loads must not sit on the chain:
+// all threads stage a batch of aggregates in shared memory (coalesced), then warp 0 walks it.
+constexpr int kCarryThreads = 256;
+
 template <class Elem>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kCarryThreads)
 scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, ScanArgs a,
-                  const double* __restrict__ tile_buf, double* __restrict__ tile_start) {
+                  const double* __restrict__ tile_buf, double* __restrict__ tile_start, int batch) {
   using Map = typename Elem::Map;
   using State = typename Elem::State;
   constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
   const DevProblem& P = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
-  const int n = threadIdx.x, M = P.M;
-  if (n >= M) return;
+  const int tid = threadIdx.x, M = P.M;
+  extern __shared__ double sm[];                 // [batch][M][W]
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  Elem el(P, St, n);
+  const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W;
+  double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW;
+  const bool walker = tid < M;
+  Elem el(P, St, walker ? tid : 0);
   State s;
-  el.init(s, a.init, a.kinit);
-  const double* src = tile_buf + ((size_t)blockIdx.x * ntiles * M + n) * W;
-  double* dst = tile_start + ((size_t)blockIdx.x * ntiles * M + n) * SW;
-  const size_t stride = (size_t)M * W, dstride = (size_t)M * SW;
-  // the walk is latency bound: keep the next aggregates in flight
-  Map cur, nxt;
-  Elem::load_map(cur, src);
-  for (long long t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) Elem::load_map(nxt, src + (size_t)(t + 1) * stride);
-    Elem::store_state(s, dst + (size_t)t * dstride);
-    Elem::apply(cur, s);
-    cur = nxt;
+  if (walker) el.init(s, a.init, a.kinit);
+  for (long long t0 = 0; t0 < ntiles; t0 += batch) {
+    const int cnt = (int)((ntiles - t0 < batch) ? ntiles - t0 : batch);
+    const size_t words = (size_t)cnt * M * W;
+    for (size_t i = tid; i < words; i += kCarryThreads) sm[i] = src[(size_t)t0 * M * W + i];
+    __syncthreads();
+    if (walker) {
+      for (int j = 0; j < cnt; ++j) {
+        Map e;
+        Elem::load_map(e, sm + ((size_t)j * M + tid) * W);
+        Elem::store_state(s, dst + ((size_t)(t0 + j) * M + tid) * SW);
+        Elem::apply(e, s);
+      }
+    }
+    __syncthreads();
   }
-  el.store_final(s);               // the state after the last step (used by a following tile / rank)
+  if (walker) el.store_final(s);   // the state after the last step (used by a following tile / rank)
 }
 
 template <class Elem>
@@ -128,22 +138,28 @@ __global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const De
   const DevProblem& P = probs[blockIdx.y];
   const DevState& St = states[blockIdx.y];
   const int n = threadIdx.x, c = threadIdx.y, M = P.M, CH = a.CH;
-  extern __shared__ double sm[];                 // [CH][M][SW] states entering each chunk
+  extern __shared__ double sm[];                 // [CH][M][SW] states entering each chunk | [CH][M][W] chunk maps
   const long long nchunks = scan_num_chunks(a.nsteps);
   const long long ntiles = scan_num_tiles(a.nsteps, CH);
   const long long first = (long long)blockIdx.x * CH;
+  const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
+  double* s_state = sm;
+  double* s_map = sm + (size_t)CH * M * SW;
+  {
+    // stage this tile's chunk aggregates (contiguous in HBM) so the walk below runs from shared memory
+    const double* src = chunk_buf + ((size_t)blockIdx.y * nchunks + first) * M * W;
+    const int nthreads = blockDim.x * blockDim.y, tid = c * blockDim.x + n;
+    for (int i = tid; i < cnt * M * W; i += nthreads) s_map[i] = src[i];
+  }
+  __syncthreads();
   if (c == 0 && n < M) {
-    const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
     State s;
     Elem::load_state(s, tile_start + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * SW);
-    const double* src = chunk_buf + (((size_t)blockIdx.y * nchunks + first) * M + n) * W;
-    Map cur, nxt;
-    Elem::load_map(cur, src);
     for (int j = 0; j < cnt; ++j) {
-      if (j + 1 < cnt) Elem::load_map(nxt, src + (size_t)(j + 1) * M * W);
-      Elem::store_state(s, sm + ((size_t)j * M + n) * SW);
-      Elem::apply(cur, s);
-      cur = nxt;
+      Map e;
+      Elem::load_map(e, s_map + ((size_t)j * M + n) * W);
+      Elem::store_state(s, s_state + ((size_t)j * M + n) * SW);
+      Elem::apply(e, s);
     }
   }
   __syncthreads();
@@ -151,7 +167,7 @@ __global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const De
   if (n >= M || chunk >= nchunks) return;
   Elem el(P, St, n);
   State s;
-  Elem::load_state(s, sm + ((size_t)c * M + n) * SW);
+  Elem::load_state(s, s_state + ((size_t)c * M + n) * SW);
   const long long s0 = chunk * kScanSteps;
   const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
   for (long long t = s0; t < s1; ++t) el.step(a.kfirst + a.dir * t, s);
