@@ -163,6 +163,17 @@ int nsagp_ep_ihgp(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep
 int nsagp_ep_full(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep,
                   const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
 
+/* gf_giekf_modulator_nmf_constraints (gf_giekf_modulator_nmf_constraints.m:144-327 predict mode,
+ * :332-484 energy of the nlZ mode as every caller runs it, GradObj = 'off'): globally iterated
+ * extended Kalman filter + RTS smoother with the hard-wired measurement y = (H_z x)' W softplus(H_g x)
+ * (:490-513, iekf_update1.m:110-117).  The covariance is dense here.  W is D-by-N column-major,
+ * sigma2 = exp(lik_param).  Predict mode: model.A/Q from lti_disc; energy mode (NSAGP_MODE_NLZ):
+ * model.A = expm(F), model.Q = Pinf - A Pinf A' (:376-380), result in out->edata (NaN and
+ * NSAGP_ERR_NAN when the innovation variance is not positive, :417-427).  Outputs used: Eft, Varft,
+ * lb, ub, MF, MS, maxDiffP[g_iter] (over the marginal variances), PF/PS as DENSE n-by-n-by-T. */
+int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
+                const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
+
 /* Batched forms: B independent problems of equal shapes (clips x hyper-parameter
  * grid x finite-difference perturbations; what fminunc does around the nlZ mode,
  * demo_toy_modulators_nmf.m:100-104).  models/liks/tables/outs are arrays of B

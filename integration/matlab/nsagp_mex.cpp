@@ -10,6 +10,7 @@
 // entry-point names and argument lists):
 //   out = nsagp_mex('ep_ihgp', model, lik, ep, tables, yall, mode)
 //   out = nsagp_mex('ep_full', model, lik, ep, [],     yall, mode)
+//   out = nsagp_mex('giekf', model, W, sigma2, g_iter, l_iter, yall, mode)
 //   [lZ, dlZ, d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)
 // model  : struct with fields D, N, bz, bg, A, Q, Pinf, h   (packed per-latent blocks, see nsagp_model)
 // lik    : struct with fields kind, sn2, link_shift, W (D-by-N), wn (1-by-S), xn (N-by-S)
@@ -119,6 +120,33 @@ void ep_call(bool ihgp, int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs
   plhs[0] = s;
 }
 
+void giekf_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: out = nsagp_mex('giekf', model, W, sigma2, g_iter, l_iter, yall, mode)");
+  (void)nlhs;
+  nsagp_model model;
+  fill_model(prhs[1], &model);
+  const double* W = dbl(prhs[2], "W");
+  const double sigma2 = mxGetScalar(prhs[3]);
+  const int32_t g_iter = (int32_t)mxGetScalar(prhs[4]), l_iter = (int32_t)mxGetScalar(prhs[5]);
+  const double* y = dbl(prhs[6], "yall");
+  const int64_t T = (int64_t)mxGetNumberOfElements(prhs[6]);
+  const int32_t mode = (int32_t)mxGetScalar(prhs[7]);
+  const mwSize M = model.D + model.N, n = model.D * model.bz + model.N * model.bg;
+  mxArray* s = mxCreateStructMatrix(1, 1, 0, nullptr);
+  nsagp_outputs o;
+  std::memset(&o, 0, sizeof(o));
+  if (mode == NSAGP_MODE_PREDICT) {
+    put(s, "Eft", M, T, &o.Eft); put(s, "Varft", M, T, &o.Varft); put(s, "lb", M, T, &o.lb); put(s, "ub", M, T, &o.ub);
+    put(s, "MF", n, T, &o.MF); put(s, "MS", n, T, &o.MS); put(s, "maxDiffP", 1, g_iter, &o.maxDiffP);
+    check(nsagp_giekf(&model, W, sigma2, g_iter, l_iter, y, T, mode, &o));
+  } else {
+    put(s, "edata", 1, 1, &o.edata);
+    const int st = nsagp_giekf(&model, W, sigma2, g_iter, l_iter, y, T, mode, &o);
+    if (st != NSAGP_ERR_NAN) check(st);          // a NaN energy is a value the reference returns to the optimiser
+  }
+  plhs[0] = s;
+}
+
 void mom_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: [lZ,dlZ,d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)");
   nsagp_lik lik;
@@ -144,6 +172,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   const std::string c(cmd);
   if (c == "ep_ihgp") ep_call(true, nlhs, plhs, nrhs, prhs);
   else if (c == "ep_full") ep_call(false, nlhs, plhs, nrhs, prhs);
+  else if (c == "giekf") giekf_call(nlhs, plhs, nrhs, prhs);
   else if (c == "mom") mom_call(nlhs, plhs, nrhs, prhs);
   else if (c == "version") plhs[0] = mxCreateString(nsagp_version());
   else mexErrMsgIdAndTxt("nsagp:arg", "unknown command '%s'", cmd);

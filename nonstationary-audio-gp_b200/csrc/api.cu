@@ -16,6 +16,7 @@
 #include "gfep.cuh"
 #include "mombatch.cuh"
 #include "adfcta.cuh"
+#include "ekf.cuh"
 
 using namespace nsagp;
 
@@ -865,6 +866,7 @@ int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
 }  // namespace
 
 #include "api_full.inc"
+#include "api_ekf.inc"
 
 extern "C" {
 
@@ -992,6 +994,11 @@ static int run_hostbuf(int kind, int32_t B, const nsagp_model* models, const nsa
   for (int b = 0; b < B && !rc; ++b) rc = nsagp_plan_fetch(pl, b, &outs[b]);
   nsagp_plan_destroy(pl);
   return rc;
+}
+
+int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
+                const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
+  return giekf_impl(model, W, sigma2, g_iter, l_iter, y, T, mode, out);
 }
 
 int nsagp_ep_ihgp(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep, const nsagp_tables* tables,

@@ -307,3 +307,58 @@ def ihgp_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, nu
     return _run(_lib.KIND_IHGP, w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, ep_fraction,
                 ep_damping, ep_itts, (constraints, w_fixed, tune_hypers), True, nargout, False,
                 nlz_mode=_lib.MODE_NLZ_RUNNING, adf_form=adf_form)
+
+
+def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
+                                       g_iter, l_iter, constraints, w_fixed, tune_hypers, nargout=6, debug_cov=False):
+    """Globally iterated EKF + RTS smoother, the comparison variant of the EP entry points.
+    Drop-in for matlab/gf_giekf_modulator_nmf_constraints.m with GradObj = 'off' (how every caller
+    runs it, experiments/train_model.m:226,239-240): ``(energy, zeros)`` when ``xt`` is empty,
+    otherwise ``(Eft, Varft, Covft, lb, ub, out)``.  ``mom`` is ignored, as in the reference
+    (its measurement model is hard-wired, :133-138)."""
+    import scipy.linalg as sla
+    yall, return_ind = merge_inputs(x, y, xt)
+    lik_param, param1, param2, Wnmf = _unpack_constrained(w, num_lik_params, D, N, constraints, w_fixed, tune_hypers)
+    F, L, Qc, H, Pinf = ss(x, param1, param2, kernel1, kernel2)[:5]
+    F, L, H, Pinf = ssmodel.balance(F, L, H, Pinf)                      # :113-120
+    sigma2 = float(np.exp(np.asarray(lik_param, float).ravel()[0]))
+    predict = xt is not None and np.size(xt) > 0
+    if predict:
+        A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)                          # :161
+    else:
+        A = sla.expm(F)                                                 # :376-380
+        Q = Pinf - A @ Pinf @ A.T
+    mdl = ssmodel.to_block_model(A, Q, H, Pinf, D, N)
+    T, M, n = yall.size, mdl.M, mdl.n
+    arrs = [_lib.as_f64(a) for a in (mdl.A, mdl.Q, mdl.Pinf, mdl.h)]
+    cm = _lib.Model()
+    cm.D, cm.N, cm.bz, cm.bg = mdl.D, mdl.N, mdl.bz, mdl.bg
+    cm.A, cm.Q, cm.Pinf, cm.h = [_lib.dptr(a) for a in arrs]
+    Wf = np.asfortranarray(np.asarray(Wnmf, float))
+    o = _lib.Outputs()
+    bufs = {}
+    if predict:
+        names = ["Eft", "Varft", "lb", "ub", "MS", "MF", "maxDiffP"] + (["PS", "PF"] if debug_cov else [])
+        shapes = dict(Eft=(T, M), Varft=(T, M), lb=(T, M), ub=(T, M), MS=(T, n), MF=(T, n), maxDiffP=(int(g_iter),),
+                      PS=(T, n, n), PF=(T, n, n))
+    else:
+        names, shapes = ["edata"], dict(edata=(1,))
+    for nm in names:
+        bufs[nm] = np.zeros(shapes[nm])
+        setattr(o, nm, _lib.dptr(bufs[nm]))
+    yb = _lib.as_f64(yall)
+    status = _lib.lib().nsagp_giekf(C.byref(cm), Wf.ctypes.data_as(_lib.c_double_p), sigma2, int(g_iter), int(l_iter),
+                                    _lib.dptr(yb), T, _lib.MODE_PREDICT if predict else _lib.MODE_NLZ, C.byref(o))
+    if not predict:
+        if status == -5:                                                # NSAGP_ERR_NAN: the reference returns NaN (:417-427)
+            return float("nan"), np.zeros(np.size(w))
+        _lib.check(status)
+        return float(bufs["edata"][0]), np.zeros(np.size(w))
+    _lib.check(status)
+    sel = lambda a: a.T[:, return_ind]
+    out = dict(MS=bufs["MS"].T, MF=bufs["MF"].T, maxDiffP=bufs["maxDiffP"], R=np.zeros((M, T)))
+    if debug_cov:
+        out["PS"] = np.transpose(bufs["PS"], (2, 1, 0))                 # (n, n, T), column-major blocks on the device
+        out["PF"] = np.transpose(bufs["PF"], (2, 1, 0))
+    res = (sel(bufs["Eft"]), sel(bufs["Varft"]), None, sel(bufs["lb"]), sel(bufs["ub"]), out)
+    return res[:max(nargout, 1)] if nargout < 6 else res
