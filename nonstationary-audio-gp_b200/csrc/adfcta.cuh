@@ -290,7 +290,7 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
 }
 
 // ------------------------------------------------------------ full-state EP
-// One CTA per signal, steps 0..T-1 (gf_ep_modulator_nmf.m:126-184; nlZ mode :400-447).
+// One CTA per signal, steps k0..T-1 (gf_ep_modulator_nmf.m:126-184; nlZ mode :400-447).
 // mom_all: moment matching at every observed step (first EP iteration) or only at
 // k == T-1.  nlz: nlZ-mode rules (clamp at every step, :425).  The measurement
 // update is written in the z-form for every site (:162-169 / :428-433), which is
@@ -298,7 +298,7 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
 template <int DPT, int BM, bool SINGLE>
 __global__ void __launch_bounds__(32 + kAdfMaxMomThreads)
 gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
-                       int mom_all, double ep_damp, int nlz, int store) {
+                       long long k0, int mom_all, double ep_damp, int nlz, int store) {
   constexpr int NVP = MomCta<DPT>::NVP;
   const DevProblem& P_ = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
@@ -319,7 +319,7 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
   const MomParams mp = make_mom_params(P_, P_.W, s_wn, s_xn);
 
   if (tid >= 32) {
-    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, 0, T, mom_all, true, s_mom, tid - 32, nmt, nthreads);
+    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, T, mom_all, true, s_mom, tid - 32, nmt, nthreads);
     return;
   }
 
@@ -339,9 +339,16 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
   const int off = P_.off[n];
   const int b = P_.off[n + 1] - off;
 
-  double y_nx = St.y[0];
-  double tt_nx = St.ttau[n];
-  double tn_nx = St.tnu[n];
+  if (k0 > 0) {                                        // continue from the stored estimate of step k0-1
+#pragma unroll
+    for (int i = 0; i < BM; ++i) m[i] = (i < b) ? St.MS[(k0 - 1) * P_.n + off + i] : 0.0;
+    const double* src = St.PS + ((size_t)(k0 - 1) * M + n) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) P[i] = src[i];
+  }
+  double y_nx = St.y[k0];
+  double tt_nx = St.ttau[k0 * M + n];
+  double tn_nx = St.tnu[k0 * M + n];
   bool pend = false, pend_obs = false, pend_mom = false;
   long long pk = 0;
   double p_tt = 0.0, p_tn = 0.0, p_Z = 1.0;
@@ -375,7 +382,7 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
     }
   };
 
-  for (long long k = 0; k < T; ++k) {
+  for (long long k = k0; k < T; ++k) {
     const double y = y_nx;
     const double tt_ld = tt_nx, tn_ld = tn_nx;
     const bool obs = !isnan(y);                          // :135 (uniform over the CTA)

@@ -565,7 +565,7 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
   if ((rc = pl->arena.upload(&pl->d_probs, pl->h_probs)) || (rc = pl->arena.upload(&pl->d_states, pl->h_states)))
     return cleanup(rc);
   const long long nchunks = scan_num_chunks(T);
-  const size_t map_d = (kind == 0) ? (size_t)(BM * BM + BM) : (size_t)(2 * BM * BM + BM);
+  const size_t map_d = (kind == 0) ? (size_t)(BM * BM + BM) : (size_t)(3 * BM * BM + 2 * BM);   // largest scan element
   const size_t state_d = (kind == 0) ? (size_t)BM : (size_t)(BM * BM + BM);
   const long long ntiles_max = scan_num_tiles(T, 1);        // CH >= 1
   if ((rc = pl->arena.alloc(&pl->d_chunk, (size_t)B * nchunks * M * map_d)) ||
@@ -765,10 +765,10 @@ int scan_ch(const nsagp_plan* pl, int map_doubles) {
 }
 
 template <class Elem>
-int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit) {
+int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags = 0) {
   if (nsteps <= 0) return NSAGP_OK;
   ScanArgs a;
-  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit;
+  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.flags = flags;
   a.CH = scan_ch(pl, Elem::kMapDoubles);
   {
     // registers: a CTA tile of 32*CH threads must fit the SM's 64 K registers

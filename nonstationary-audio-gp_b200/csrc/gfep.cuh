@@ -53,7 +53,7 @@ __device__ __forceinline__ void mat_mul_bt_add(const double* A, const double* B,
 template <int DP, int BM>
 __global__ void __launch_bounds__(32)
 gfep_filter_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
-                   int mom_all, double ep_damp, int nlz, int store) {
+                   long long k0, int mom_all, double ep_damp, int nlz, int store) {
   const DevProblem& P_ = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
   const int lane = threadIdx.x;
@@ -86,8 +86,15 @@ gfep_filter_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
   for (int i = 0; i < BM; ++i) { hv[i] = P_.h[n * BM + i]; m[i] = 0.0; }   // :116
   const int off = P_.off[n];
   const int b = P_.off[n + 1] - off;
+  if (k0 > 0) {                                        // continue from the stored estimate of step k0-1
+#pragma unroll
+    for (int i = 0; i < BM; ++i) m[i] = (i < b) ? St.MS[(k0 - 1) * P_.n + off + i] : 0.0;
+    const double* src = St.PS + ((size_t)(k0 - 1) * M + n) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) P[i] = src[i];
+  }
 
-  for (long long k = 0; k < T; ++k) {
+  for (long long k = k0; k < T; ++k) {
     if (k > 0) {                                       // :129-132
       double t[BM], AP[BM * BM];
 #pragma unroll
@@ -397,7 +404,7 @@ struct RtsScanElem {
   RtsElem<BM> el;
   bool ok;
   double mdM, mdP;
-  __device__ RtsScanElem(const DevProblem& P_, const DevState& S_, int n_) : el(P_, S_, n_), ok(true), mdM(0.0), mdP(0.0) {}
+  __device__ RtsScanElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : el(P_, S_, n_), ok(true), mdM(0.0), mdP(0.0) {}
   __device__ static __forceinline__ void compose(Map& acc, const Map& e) { rts_compose<BM>(acc, e); }
   __device__ static __forceinline__ void apply(const Map& e, State& s) { rts_apply_map<BM>(e, s.m, s.P); }
   __device__ static __forceinline__ void store_map(const Map& e, double* dst) {
@@ -469,6 +476,286 @@ struct RtsScanElem {
     atomic_max_nonneg(el.St.maxdiff, mdM);
     atomic_max_nonneg(el.St.maxdiff + 1, mdP);
   }
+};
+
+// ------------------------------------------------------- frozen-site filter scan
+// Once the sites are frozen (every filter pass after the first, except its last step), the
+// block filter of gf_ep_modulator_nmf.m:126-184 is a linear Kalman filter with per-step
+// pseudo-observations (precision ttau_k, natural mean tnu_k), and its steps are the elements
+// a_k = (A, b, C, eta, J) of Sarkka & Garcia-Fernandez (2021), written here on the natural
+// parameters so that ttau = 0 (site at the bound, or a missing sample) needs no special case:
+//   z = ttau h Q h' + 1
+//   A_k = (I - Q h' h ttau / z) A      b_k = Q h' tnu / z      C_k = Q - Q h' h Q ttau / z
+//   eta_k = A' h' tnu / z              J_k = A' h' h A ttau / z
+// The first step has no prediction: it is the element (0, m_post, P_post, 0, 0) of the prior.
+template <int BM>
+struct KfMap {
+  double A[BM * BM], b[BM], C[BM * BM], eta[BM], J[BM * BM];
+};
+
+// X <- inverse of X (BM-by-BM, column-major), Gauss-Jordan with partial pivoting done by
+// conditional row swaps so that every index is a compile-time constant (registers, no local memory).
+template <int BM>
+__device__ __forceinline__ void small_inverse(double (&X)[BM * BM], double (&Y)[BM * BM]) {
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) Y[i] = ((i % BM) == (i / BM)) ? 1.0 : 0.0;
+#pragma unroll
+  for (int j = 0; j < BM; ++j) {
+#pragma unroll
+    for (int r = j + 1; r < BM; ++r) {
+      const bool sw = fabs(X[r + j * BM]) > fabs(X[j + j * BM]);
+#pragma unroll
+      for (int c = 0; c < BM; ++c) {
+        const double xa = X[j + c * BM], xb = X[r + c * BM];
+        X[j + c * BM] = sw ? xb : xa; X[r + c * BM] = sw ? xa : xb;
+        const double ya = Y[j + c * BM], yb = Y[r + c * BM];
+        Y[j + c * BM] = sw ? yb : ya; Y[r + c * BM] = sw ? ya : yb;
+      }
+    }
+    const double piv = 1.0 / X[j + j * BM];
+#pragma unroll
+    for (int c = 0; c < BM; ++c) { X[j + c * BM] *= piv; Y[j + c * BM] *= piv; }
+#pragma unroll
+    for (int r = 0; r < BM; ++r) {
+      if (r != j) {
+        const double f = X[r + j * BM];
+#pragma unroll
+        for (int c = 0; c < BM; ++c) {
+          X[r + c * BM] = fma(-f, X[j + c * BM], X[r + c * BM]);
+          Y[r + c * BM] = fma(-f, Y[j + c * BM], Y[r + c * BM]);
+        }
+      }
+    }
+  }
+}
+
+// y = X v ; y = X' v
+template <int BM>
+__device__ __forceinline__ void mat_vec(const double* X, const double* v, double* y) {
+#pragma unroll
+  for (int i = 0; i < BM; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < BM; ++j) s = fma(X[i + j * BM], v[j], s);
+    y[i] = s;
+  }
+}
+template <int BM>
+__device__ __forceinline__ void mat_t_vec(const double* X, const double* v, double* y) {
+#pragma unroll
+  for (int i = 0; i < BM; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < BM; ++j) s = fma(X[j + i * BM], v[j], s);
+    y[i] = s;
+  }
+}
+// C = A' * B
+template <int BM>
+__device__ __forceinline__ void mat_t_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < BM; ++j)
+#pragma unroll
+    for (int i = 0; i < BM; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < BM; ++l) s = fma(A[l + i * BM], B[l + j * BM], s);
+      C[i + j * BM] = s;
+    }
+}
+
+// acc <- e o acc  (acc earlier in time, e later): Sarkka & Garcia-Fernandez (2021), eq. for a_i (x) a_j
+template <int BM>
+__device__ __forceinline__ void kf_compose(KfMap<BM>& acc, const KfMap<BM>& e) {
+  double X[BM * BM], Mx[BM * BM], T1[BM * BM], T2[BM * BM];
+  mat_mul<BM>(acc.C, e.J, X);                               // I + C_i J_j
+#pragma unroll
+  for (int i = 0; i < BM; ++i) X[i + i * BM] += 1.0;
+  small_inverse<BM>(X, Mx);
+  double v[BM], u[BM], w[BM];
+  mat_vec<BM>(acc.C, e.eta, v);                             // b_i + C_i eta_j
+#pragma unroll
+  for (int i = 0; i < BM; ++i) v[i] += acc.b[i];
+  mat_vec<BM>(Mx, v, u);
+  double bn[BM];
+  mat_vec<BM>(e.A, u, bn);
+  mat_vec<BM>(e.J, acc.b, v);                               // eta_j - J_j b_i
+#pragma unroll
+  for (int i = 0; i < BM; ++i) v[i] = e.eta[i] - v[i];
+  mat_t_vec<BM>(Mx, v, w);                                  // (I + J_j C_i)^-1 = Mx'
+  double en[BM];
+  mat_t_vec<BM>(acc.A, w, en);
+  mat_mul<BM>(Mx, acc.C, T1);                               // C_ij = A_j Mx C_i A_j' + C_j
+  mat_mul<BM>(e.A, T1, T2);
+  double Cn[BM * BM];
+  mat_mul_bt_add<BM>(T2, e.A, e.C, Cn);
+  mat_mul<BM>(e.J, acc.A, T1);                              // J_ij = A_i' Mx' J_j A_i + J_i
+  mat_t_mul<BM>(Mx, T1, T2);
+  double Jn[BM * BM];
+  mat_t_mul<BM>(acc.A, T2, Jn);
+  mat_mul<BM>(Mx, acc.A, T1);                               // A_ij = A_j Mx A_i
+  mat_mul<BM>(e.A, T1, T2);
+#pragma unroll
+  for (int i = 0; i < BM * BM; ++i) { acc.A[i] = T2[i]; acc.C[i] = Cn[i]; acc.J[i] = Jn[i] + acc.J[i]; }
+#pragma unroll
+  for (int i = 0; i < BM; ++i) { acc.b[i] = bn[i] + e.b[i]; acc.eta[i] = en[i] + acc.eta[i]; }
+}
+
+// (m, P) <- the filtered moments after the steps of e, given the moments (m, P) before them.
+template <int BM>
+__device__ __forceinline__ void kf_apply(const KfMap<BM>& e, double (&m)[BM], double (&Pm)[BM * BM]) {
+  double X[BM * BM], Mx[BM * BM], T1[BM * BM], T2[BM * BM], v[BM], u[BM];
+  mat_mul<BM>(Pm, e.J, X);
+#pragma unroll
+  for (int i = 0; i < BM; ++i) X[i + i * BM] += 1.0;
+  small_inverse<BM>(X, Mx);
+  mat_vec<BM>(Pm, e.eta, v);
+#pragma unroll
+  for (int i = 0; i < BM; ++i) v[i] += m[i];
+  mat_vec<BM>(Mx, v, u);
+  mat_vec<BM>(e.A, u, v);
+#pragma unroll
+  for (int i = 0; i < BM; ++i) m[i] = v[i] + e.b[i];
+  mat_mul<BM>(Mx, Pm, T1);
+  mat_mul<BM>(e.A, T1, T2);
+  mat_mul_bt_add<BM>(T2, e.A, e.C, Pm);
+}
+
+template <int BM>
+struct KfScanElem {
+  using Map = KfMap<BM>;
+  using State = RtsState<BM>;
+  static constexpr int kMapDoubles = 3 * BM * BM + 2 * BM;
+  static constexpr int kStateDoubles = BM * BM + BM;
+  const DevProblem& P; const DevState& St; int n, off, b; bool nlz;
+  double A[BM * BM], Q[BM * BM], hv[BM], hA[BM], Qh[BM], hQh;
+  __device__ KfScanElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs& a)
+      : P(P_), St(S_), n(n_), nlz((a.flags & 1) != 0) {
+    off = P.off[n]; b = P.off[n + 1] - off;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) { A[i] = P.A[n * BM * BM + i]; Q[i] = P.Q[n * BM * BM + i]; }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) { hv[i] = P.h[n * BM + i]; hA[i] = P.hA[n * BM + i]; }
+    mat_vec<BM>(Q, hv, Qh);
+    hQh = 0.0;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) hQh = fma(hv[i], Qh[i], hQh);
+  }
+  __device__ static __forceinline__ void compose(Map& acc, const Map& e) { kf_compose<BM>(acc, e); }
+  __device__ static __forceinline__ void apply(const Map& e, State& s) { kf_apply<BM>(e, s.m, s.P); }
+  __device__ static __forceinline__ void store_map(const Map& e, double* d) {
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) { d[i] = e.A[i]; d[BM * BM + i] = e.C[i]; d[2 * BM * BM + i] = e.J[i]; }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) { d[3 * BM * BM + i] = e.b[i]; d[3 * BM * BM + BM + i] = e.eta[i]; }
+  }
+  __device__ static __forceinline__ void load_map(Map& e, const double* d) {
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) { e.A[i] = d[i]; e.C[i] = d[BM * BM + i]; e.J[i] = d[2 * BM * BM + i]; }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) { e.b[i] = d[3 * BM * BM + i]; e.eta[i] = d[3 * BM * BM + BM + i]; }
+  }
+  __device__ static __forceinline__ void store_state(const State& s, double* dst) { RtsScanElem<BM>::store_state(s, dst); }
+  __device__ static __forceinline__ void load_state(State& s, const double* src) { RtsScanElem<BM>::load_state(s, src); }
+  // sites of step k as the frozen pass sees them (:159-176; nlZ mode clamps at every step, :425)
+  __device__ __forceinline__ bool sites(long long k, double& tt, double& tn) const {
+    if (isnan(St.y[k])) { tt = 0.0; tn = 0.0; return false; }                  // :135 no update at all
+    tt = St.ttau[k * P.M + n]; tn = St.tnu[k * P.M + n];
+    if (nlz) tt = fmax(tt, 0.0);
+    return true;
+  }
+  __device__ __forceinline__ void get(long long k, Map& e) {
+    double tt, tn;
+    sites(k, tt, tn);
+    if (k == 0) {                                           // prior (0, Pinf), update only (:116-117,:129)
+      double W0[BM], s0 = 0.0;
+      const double* Pi = P.Pinf + n * BM * BM;
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < BM; ++j) w = fma(Pi[i + j * BM], hv[j], w);
+        W0[i] = w;
+      }
+#pragma unroll
+      for (int i = 0; i < BM; ++i) s0 = fma(hv[i], W0[i], s0);
+      const double rz = 1.0 / fma(tt, s0, 1.0);
+#pragma unroll
+      for (int j = 0; j < BM; ++j)
+#pragma unroll
+        for (int i = 0; i < BM; ++i) {
+          e.A[i + j * BM] = 0.0; e.J[i + j * BM] = 0.0;
+          e.C[i + j * BM] = fma(-(W0[i] * (tt * rz)), W0[j], Pi[i + j * BM]);
+        }
+#pragma unroll
+      for (int i = 0; i < BM; ++i) { e.b[i] = W0[i] * (tn * rz); e.eta[i] = 0.0; }
+      return;
+    }
+    const double rz = 1.0 / fma(tt, hQh, 1.0);
+    const double g = tt * rz, c = tn * rz;
+#pragma unroll
+    for (int j = 0; j < BM; ++j)
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        e.A[i + j * BM] = fma(-(Qh[i] * g), hA[j], A[i + j * BM]);
+        e.C[i + j * BM] = fma(-(Qh[i] * g), Qh[j], Q[i + j * BM]);
+        e.J[i + j * BM] = (hA[i] * g) * hA[j];
+      }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) { e.b[i] = Qh[i] * c; e.eta[i] = hA[i] * c; }
+  }
+  // the reference's literal step: predict (k > 0), z-form update, store (:129-182)
+  __device__ __forceinline__ void step(long long k, State& s) {
+    if (k > 0) {
+      double t[BM], AP[BM * BM];
+      mat_vec<BM>(A, s.m, t);
+#pragma unroll
+      for (int i = 0; i < BM; ++i) s.m[i] = t[i];
+      mat_mul<BM>(A, s.P, AP);
+      mat_mul_bt_add<BM>(AP, A, Q, s.P);
+    }
+    double tt, tn;
+    if (sites(k, tt, tn)) {
+      double fmu = 0.0, HPH = 0.0, Wv[BM], hP[BM];
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        fmu = fma(hv[i], s.m[i], fmu);
+        double w = 0.0, g = 0.0;
+#pragma unroll
+        for (int j = 0; j < BM; ++j) {
+          w = fma(s.P[i + j * BM], hv[j], w);
+          g = fma(hv[j], s.P[j + i * BM], g);
+        }
+        Wv[i] = w; hP[i] = g;
+      }
+#pragma unroll
+      for (int i = 0; i < BM; ++i) HPH = fma(hP[i], hv[i], HPH);
+      if (nlz && !(HPH > 0.0)) atomicCAS(St.status, 0, 2);                     // `keyboard` trap (:408-410)
+      if (nlz) St.ttau[k * P.M + n] = tt;                                      // the clamp is stored (:425)
+      const double rz = 1.0 / fma(tt, HPH, 1.0);
+      const double c = (tn - tt * fmu) * rz, g = tt * rz;
+#pragma unroll
+      for (int i = 0; i < BM; ++i) s.m[i] = fma(Wv[i], c, s.m[i]);
+#pragma unroll
+      for (int j = 0; j < BM; ++j)
+#pragma unroll
+        for (int i = 0; i < BM; ++i) s.P[i + j * BM] = fma(-(Wv[i] * g), hP[j], s.P[i + j * BM]);
+    }
+#pragma unroll
+    for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P.n + off + i] = s.m[i];
+    double* dst = St.PS + ((size_t)k * P.M + n) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) dst[i] = s.P[i];
+  }
+  __device__ __forceinline__ void init(State& s, int, long long) {            // (0, Pinf); step 0 does not predict
+#pragma unroll
+    for (int i = 0; i < BM; ++i) s.m[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) s.P[i] = P.Pinf[n * BM * BM + i];
+  }
+  __device__ __forceinline__ void store_final(const State&) {}
+  __device__ __forceinline__ void finish_reduce() {}
+  __device__ __forceinline__ void finish_apply() {}
 };
 
 }  // namespace nsagp

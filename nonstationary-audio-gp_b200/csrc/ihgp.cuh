@@ -266,7 +266,7 @@ struct FilterElem : AffineElemBase<BM> {
   using State = MeanState<BM>;
   const DevProblem& P; const DevState& St; int n, off, b, hint;
   double A[BM * BM], hA[BM];
-  __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_), hint(0) {
+  __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), hint(0) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
@@ -329,7 +329,7 @@ struct SmootherElem : AffineElemBase<BM> {
   const DevProblem& P; const DevState& St; int n, off, b, hint;
   double A[BM * BM], hv[BM];
   double mdM;
-  __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_), hint(0), mdM(0.0) {
+  __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), hint(0), mdM(0.0) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];

@@ -34,6 +34,7 @@ struct ScanArgs {
   int init;                        // Elem-specific initial-state selector
   long long kinit;
   int CH;                          // chunks per CTA tile (blockDim.y)
+  int flags;                       // Elem-specific (bit 0: nlZ-mode rules of the full-state filter)
 };
 
 __host__ __device__ inline long long scan_num_chunks(long long nsteps) { return (nsteps + kScanSteps - 1) / kScanSteps; }
@@ -58,7 +59,7 @@ __global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const D
   if (n < M) {
     Map acc;
     if (live) {
-      Elem el(P, St, n);
+      Elem el(P, St, n, a);
       Map e;
       const long long s0 = chunk * kScanSteps;
       const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
@@ -107,7 +108,7 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W;
   double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW;
   const bool walker = tid < M;
-  Elem el(P, St, walker ? tid : 0);
+  Elem el(P, St, walker ? tid : 0, a);
   State s;
   if (walker) el.init(s, a.init, a.kinit);
   for (long long t0 = 0; t0 < ntiles; t0 += batch) {
@@ -165,7 +166,7 @@ __global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const De
   __syncthreads();
   const long long chunk = first + c;
   if (n >= M || chunk >= nchunks) return;
-  Elem el(P, St, n);
+  Elem el(P, St, n, a);
   State s;
   Elem::load_state(s, s_state + ((size_t)c * M + n) * SW);
   const long long s0 = chunk * kScanSteps;
