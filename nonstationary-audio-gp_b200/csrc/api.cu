@@ -889,7 +889,13 @@ int nsagp_plan_run(nsagp_plan* pl) {
     CU(cudaMemsetAsync(St.negcav, 0, 8, g_stream));
     CU(cudaMemsetAsync(St.status, 0, 4, g_stream));
     if (St.V) CU(cudaMemsetAsync(St.V, 0, (size_t)T * pl->M * 8, g_stream));
-    CU(cudaMemcpyAsync(St.vm0, pl->h_vminf.data() + (size_t)b * pl->M, pl->M * 8, cudaMemcpyHostToDevice, g_stream));
+    if (pl->kind == 0 && T == 1) {
+      // the reference resets P to zeros before the smoother loop (ihgp_ep_modulator_nmf.m:358), and with a
+      // single time step that loop never runs: Varft = diag(H*0*H') = 0
+      CU(cudaMemsetAsync(St.vm0, 0, pl->M * 8, g_stream));
+    } else {
+      CU(cudaMemcpyAsync(St.vm0, pl->h_vminf.data() + (size_t)b * pl->M, pl->M * 8, cudaMemcpyHostToDevice, g_stream));
+    }
   }
   CU(cudaMemsetAsync(pl->d_nlZ, 0, (size_t)pl->B * (pl->ep_itts + 1) * 8, g_stream));
   CU(cudaMemsetAsync(pl->d_diag, 0, (size_t)pl->B * pl->ep_itts * 16, g_stream));
