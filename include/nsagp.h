@@ -206,6 +206,16 @@ int nsagp_plan_set_adf_form(nsagp_plan* plan, int form);
 int nsagp_plan_run(nsagp_plan* plan);
 int nsagp_plan_fetch(nsagp_plan* plan, int32_t b, nsagp_outputs* out);
 int nsagp_plan_destroy(nsagp_plan* plan);
+/* Time-chunked execution of ONE signal over several GPUs (infinite-horizon predict mode, B = 1).
+ * Every rank creates the same plan over the whole signal, declares the range [t0, t1) of time steps
+ * whose frozen-site passes it executes, and the host drives the EP schedule stage by stage, moving
+ * the O(state^2) scan aggregates, the one-step site halo and the lZ / max-diff scalars between ranks
+ * (nonstationary-audio-gp_b200/chunked.py does it with torch.distributed over NCCL).  The ADF pass
+ * (ihgp_ep_modulator_nmf.m:253-271) is a nonlinear recurrence and runs replicated on every rank.
+ * Stage numbers and their buffers: csrc/api_chunk.inc (enum ChunkStage). */
+int nsagp_plan_set_range(nsagp_plan* plan, int64_t t0, int64_t t1);
+int nsagp_plan_stage(nsagp_plan* plan, int32_t stage, double x, int64_t k, const double* in, int64_t n_in,
+                     double* out, int64_t n_out);
 /* Device time (ms, CUDA events on the launch stream) of the phases of the last
  * nsagp_plan_run: [0] total, [1] ADF filter pass, [2] fixed-site filter passes,
  * [3] smoother passes, [4] site-update passes.  Returns the number written. */

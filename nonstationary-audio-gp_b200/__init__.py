@@ -10,7 +10,7 @@ so import it with importlib:
 All time loops run in csrc/libnsagp.so (C ABI: include/nsagp.h).  Nothing here
 falls back to the CPU.
 """
-from . import _lib, batch, cubature, ssmodel, synth, tables              # noqa: F401
+from . import _lib, batch, chunked, cubature, ssmodel, synth, tables              # noqa: F401
 from ._lib import NsagpError, build                                       # noqa: F401
 from .cubature import gauher, mvhermgauss_unit, utp_ws                    # noqa: F401
 from .entry import (Plan, gf_ep_modulator_nmf, gf_ep_modulator_nmf_constraints,      # noqa: F401

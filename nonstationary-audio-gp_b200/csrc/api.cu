@@ -129,6 +129,8 @@ struct DeviceCache {
 };
 thread_local DeviceCache g_cache;
 
+constexpr int kMaxPrevShards = 16;      // aggregates of other GPUs' shards that can precede a plan's scan tiles
+
 struct DeviceArena {
   std::vector<std::pair<void*, size_t>> ptrs;
   size_t bytes = 0;
@@ -180,6 +182,8 @@ struct nsagp_plan {
   double* d_chunk = nullptr;    // scan: one map per (chunk, block)
   double* d_tile = nullptr;     // scan: one map per (CTA tile, block)
   double* d_start = nullptr;    // scan: state entering each CTA tile
+  double* d_total = nullptr;    // scan: this plan's single aggregate (time-chunked runs)
+  long long t0 = 0, t1 = -1;    // shard of the frozen-site passes this plan executes (time-chunked runs)
   double* d_nlZ = nullptr;      // [B][ep_itts + 1]  (last slot: edata)
   double* d_diag = nullptr;     // [B][ep_itts][2]
   double* d_MF = nullptr;       // [B][T][n] filtered means of the last pass (predict mode)
@@ -568,12 +572,16 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
   const size_t map_d = (kind == 0) ? (size_t)(BM * BM + BM) : (size_t)(3 * BM * BM + 2 * BM);   // largest scan element
   const size_t state_d = (kind == 0) ? (size_t)BM : (size_t)(BM * BM + BM);
   const long long ntiles_max = scan_num_tiles(T, 1);        // CH >= 1
+  // (kMaxPrevShards slots in front of the tile arrays: aggregates of other GPUs' shards, time-chunked runs)
   if ((rc = pl->arena.alloc(&pl->d_chunk, (size_t)B * nchunks * M * map_d)) ||
-      (rc = pl->arena.alloc(&pl->d_tile, (size_t)B * ntiles_max * M * map_d)) ||
-      (rc = pl->arena.alloc(&pl->d_start, (size_t)B * ntiles_max * M * state_d)) ||
+      (rc = pl->arena.alloc(&pl->d_tile, ((size_t)B * ntiles_max + kMaxPrevShards) * M * map_d)) ||
+      (rc = pl->arena.alloc(&pl->d_start, ((size_t)B * ntiles_max + kMaxPrevShards) * M * state_d)) ||
+      (rc = pl->arena.alloc(&pl->d_total, (size_t)M * map_d)) ||
       (rc = pl->arena.alloc(&pl->d_nlZ, (size_t)B * (pl->ep_itts + 1))) ||
       (rc = pl->arena.alloc(&pl->d_diag, (size_t)B * pl->ep_itts * 2)))
     return cleanup(rc);
+  pl->d_tile += (size_t)kMaxPrevShards * M * map_d;
+  pl->d_start += (size_t)kMaxPrevShards * M * state_d;
   if (predict && (rc = pl->arena.alloc(&pl->d_MF, (size_t)B * T * pl->n))) return cleanup(rc);
   cudaEventCreate(&pl->ev[0]);
   cudaEventCreate(&pl->ev[1]);
@@ -682,8 +690,9 @@ size_t lik_smem_bytes(const nsagp_plan* pl) {
   return ((size_t)pl->DP * kNP + (size_t)pl->S * (1 + kNP)) * sizeof(double);
 }
 
-int launch_sum(nsagp_plan* pl, int slot, int neg) {
-  sum_kernel<<<pl->B, 1024, 0, g_stream>>>(pl->d_states, pl->T, pl->d_nlZ, pl->ep_itts + 1, slot, neg);
+int launch_sum(nsagp_plan* pl, int slot, int neg, long long k0 = 0, long long k1 = -1) {
+  if (k1 < 0) k1 = pl->T;
+  sum_kernel<<<pl->B, 1024, 0, g_stream>>>(pl->d_states, k0, k1 - k0, pl->d_nlZ, pl->ep_itts + 1, slot, neg);
   LAUNCH_CHECK();
   return NSAGP_OK;
 }
@@ -765,31 +774,54 @@ int scan_ch(const nsagp_plan* pl, int map_doubles) {
 }
 
 template <class Elem>
-int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags = 0) {
-  if (nsteps <= 0) return NSAGP_OK;
-  ScanArgs a;
-  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.flags = flags;
+int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags) {
+  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.flags = flags; a.nprev = 0;
   a.CH = scan_ch(pl, Elem::kMapDoubles);
-  {
-    // registers: a CTA tile of 32*CH threads must fit the SM's 64 K registers
-    cudaFuncAttributes f1, f3;
-    CU(cudaFuncGetAttributes(&f1, scan_reduce_kernel<Elem>));
-    CU(cudaFuncGetAttributes(&f3, scan_apply_kernel<Elem>));
-    const int regs = std::max(f1.numRegs, f3.numRegs);
-    while (a.CH > 1 && 32 * a.CH * regs > 65536) a.CH >>= 1;
-  }
-  const long long ntiles = scan_num_tiles(nsteps, a.CH);
+  // registers: a CTA tile of 32*CH threads must fit the SM's 64 K registers
+  cudaFuncAttributes f1, f3;
+  CU(cudaFuncGetAttributes(&f1, scan_reduce_kernel<Elem>));
+  CU(cudaFuncGetAttributes(&f3, scan_apply_kernel<Elem>));
+  const int regs = std::max(f1.numRegs, f3.numRegs);
+  while (a.CH > 1 && 32 * a.CH * regs > 65536) a.CH >>= 1;
+  return NSAGP_OK;
+}
+
+// phase 1 (+ the shard aggregate on request: agg_host [M][W])
+template <class Elem>
+int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
+  const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
   const dim3 block(32, a.CH);
   const dim3 grid((unsigned)ntiles, pl->B);
   const size_t sm1 = (size_t)a.CH * pl->M * Elem::kMapDoubles * sizeof(double);
-  const size_t sm3 = (size_t)a.CH * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
   if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   scan_reduce_kernel<Elem><<<grid, block, sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile);
   LAUNCH_CHECK();
+  if (agg_host) {
+    scan_total_kernel<Elem><<<1, 32, 0, g_stream>>>(pl->d_probs, a, pl->d_tile, pl->d_total);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(agg_host, pl->d_total, (size_t)pl->M * Elem::kMapDoubles * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+  }
+  return NSAGP_OK;
+}
+
+// phases 2 and 3; prev_host: nprev aggregates [nprev][M][W] of the shards processed before this one
+template <class Elem>
+int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev) {
+  const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
+  const dim3 block(32, a.CH);
+  const dim3 grid((unsigned)ntiles, pl->B);
+  const size_t sm3 = (size_t)a.CH * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
+  if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  if (nprev > 0) {
+    if (pl->B != 1 || nprev > kMaxPrevShards) return fail(NSAGP_ERR_INVALID, "time-chunked scans need B = 1 and at most 16 shards");
+    const size_t w = (size_t)pl->M * Elem::kMapDoubles;
+    CU(cudaMemcpyAsync(pl->d_tile - (size_t)nprev * w, prev_host, (size_t)nprev * w * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  }
+  a.nprev = nprev;
   {
     const size_t per_tile = (size_t)pl->M * Elem::kMapDoubles * sizeof(double);
-    int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)ntiles, (64 * 1024) / per_tile));
+    int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)(ntiles + nprev), (64 * 1024) / per_tile));
     const size_t sm2 = per_tile * batch;
     if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(scan_carry_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     scan_carry_kernel<Elem><<<pl->B, kCarryThreads, sm2, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_tile, pl->d_start, batch);
@@ -800,6 +832,15 @@ int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int in
   return NSAGP_OK;
 }
 
+template <class Elem>
+int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags = 0) {
+  if (nsteps <= 0) return NSAGP_OK;
+  ScanArgs a;
+  int rc = scan_setup<Elem>(pl, a, kfirst, nsteps, dir, init, kinit, flags);
+  if (rc || (rc = scan_reduce<Elem>(pl, a, nullptr))) return rc;
+  return scan_finish<Elem>(pl, a, nullptr, 0);
+}
+
 template <template <int> class ElemT>
 int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit) {
   int rc = NSAGP_OK;
@@ -807,15 +848,16 @@ int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int
   return rc;
 }
 
-int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ) {
-  if (pl->T < 2) return NSAGP_OK;
+int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ, long long k0 = 0, long long k1 = -1) {
+  if (k1 < 0) k1 = pl->T - 1;
+  if (k1 <= k0) return NSAGP_OK;
   constexpr int TPB = 64;
   const size_t sm = (size_t)4 * pl->M * TPB * sizeof(double) + lik_smem_bytes(pl);
-  const dim3 grid((unsigned)((pl->T - 1 + TPB - 1) / TPB), pl->B);
+  const dim3 grid((unsigned)((k1 - k0 + TPB - 1) / TPB), pl->B);
   DISPATCH_DP(pl->DP, {
     auto kern = site_update_kernel<DP_, TPB, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, pl->T, pl->alpha, damp, write_lZ, 0);
+    kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, k0, k1, pl->alpha, damp, write_lZ, 0);
   });
   LAUNCH_CHECK();
   return NSAGP_OK;
@@ -863,18 +905,8 @@ int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
   return NSAGP_OK;
 }
 
-}  // namespace
-
-#include "api_full.inc"
-#include "api_ekf.inc"
-
-extern "C" {
-
-int nsagp_plan_run(nsagp_plan* pl) {
-  if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
-  int rc = ensure_stream();
-  if (rc) return rc;
-  // (re)initialise the mutable state so a plan can be run repeatedly
+// (re)initialise the mutable state so a plan can be run repeatedly
+int plan_reset(nsagp_plan* pl) {
   const long long T = pl->T;
   for (int b = 0; b < pl->B; ++b) {
     DevState& St = pl->h_states[b];
@@ -899,6 +931,22 @@ int nsagp_plan_run(nsagp_plan* pl) {
   }
   CU(cudaMemsetAsync(pl->d_nlZ, 0, (size_t)pl->B * (pl->ep_itts + 1) * 8, g_stream));
   CU(cudaMemsetAsync(pl->d_diag, 0, (size_t)pl->B * pl->ep_itts * 16, g_stream));
+  return NSAGP_OK;
+}
+
+}  // namespace
+
+#include "api_full.inc"
+#include "api_ekf.inc"
+#include "api_chunk.inc"
+
+extern "C" {
+
+int nsagp_plan_run(nsagp_plan* pl) {
+  if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
+  int rc = ensure_stream();
+  if (rc) return rc;
+  if ((rc = plan_reset(pl))) return rc;
   PhaseTimer tm{pl};
   CU(cudaEventRecord(pl->ev[0], g_stream));
   rc = (pl->kind == 0) ? run_ihgp(pl, tm) : run_full(pl, tm);

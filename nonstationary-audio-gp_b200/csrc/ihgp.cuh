@@ -392,7 +392,7 @@ struct SmootherElem : AffineElemBase<BM> {
 };
 
 // -------------------------------------------------------- site update (EP)
-// One thread per time step k in [0, T-1): cavity from the smoothed marginal,
+// One thread per time step k in [k0, k1) (the whole pass: [0, T-1)): cavity from the smoothed marginal,
 // moments, damped Power-EP update on sites with positive cavity variance
 // (ihgp_ep_modulator_nmf.m:397-436; gf_ep_modulator_nmf.m:236-267, :486-510).
 // FULL = false: marginal variance from the steady-state table (IHGP);
@@ -403,11 +403,11 @@ struct SmootherElem : AffineElemBase<BM> {
 template <int DP, int TPB, bool FULL>
 __global__ void __launch_bounds__(TPB)
 site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                   long long T, double alpha, double ep_damp, int write_lZ, int clamp_R) {
+                   long long k0, long long k1, double alpha, double ep_damp, int write_lZ, int clamp_R) {
   const DevProblem& P = probs[blockIdx.y];
   const DevState& St = states[blockIdx.y];
   const int tid = threadIdx.x;
-  const long long k = (long long)blockIdx.x * TPB + tid;
+  const long long k = k0 + (long long)blockIdx.x * TPB + tid;     // steps k0..k1-1 (k1 <= T-1)
   const int M = P.M, nr = P.nr;
 
   extern __shared__ double sm[];
@@ -422,7 +422,7 @@ site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
   for (int i = tid; i < P.S; i += TPB) s_wn[i] = P.wn[i];
   for (int i = tid; i < kNP * P.S; i += TPB) s_xn[i] = P.xn[i];
   __syncthreads();
-  if (k >= T - 1) return;
+  if (k >= k1) return;
   const double y = St.y[k];
   if (isnan(y)) {                          // ihgp :398, gf_ep :237
     if (!FULL && write_lZ) St.lZ[k] = 0.0; // IHGP accumulates a scalar: no term for this step
@@ -473,10 +473,11 @@ site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
   if (neg) atomicAdd(St.negcav, (unsigned long long)neg);
 }
 
-// Deterministic sum of x[0..n) into out[0] (negated if neg): one CTA per signal.
+// Deterministic sum of lZ[k0..k0+n) into out[slot] (negated if neg): one CTA per signal.
 __global__ void __launch_bounds__(1024)
-sum_kernel(const DevState* __restrict__ states, long long n, double* __restrict__ out, int stride, int slot, int neg) {
-  const double* x = states[blockIdx.x].lZ;
+sum_kernel(const DevState* __restrict__ states, long long k0, long long n, double* __restrict__ out, int stride, int slot,
+           int neg) {
+  const double* x = states[blockIdx.x].lZ + k0;
   __shared__ double sh[1024];
   double acc = 0.0;
   for (long long i = threadIdx.x; i < n; i += 1024) acc += x[i];

@@ -35,6 +35,7 @@ struct ScanArgs {
   long long kinit;
   int CH;                          // chunks per CTA tile (blockDim.y)
   int flags;                       // Elem-specific (bit 0: nlZ-mode rules of the full-state filter)
+  int nprev;                       // carry only: aggregates of preceding shards (other GPUs) placed before the tiles
 };
 
 __host__ __device__ inline long long scan_num_chunks(long long nsteps) { return (nsteps + kScanSteps - 1) / kScanSteps; }
@@ -104,9 +105,12 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   const DevState& St = states[blockIdx.x];
   const int tid = threadIdx.x, M = P.M;
   extern __shared__ double sm[];                 // [batch][M][W]
-  const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W;
-  double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW;
+  // When a signal is time-chunked over GPUs, the aggregates of the shards that come earlier in
+  // processing order sit in the nprev slots before tile_buf (single-problem plans only): the
+  // walk starts from the global initial state and passes through them first.
+  const long long ntiles = scan_num_tiles(a.nsteps, a.CH) + a.nprev;
+  const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W - (size_t)a.nprev * M * W;
+  double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW - (size_t)a.nprev * M * SW;
   const bool walker = tid < M;
   Elem el(P, St, walker ? tid : 0, a);
   State s;
@@ -127,6 +131,26 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
     __syncthreads();
   }
   if (walker) el.store_final(s);   // the state after the last step (used by a following tile / rank)
+}
+
+// The shard's single aggregate (composition of its tiles in processing order): what a GPU
+// contributes to the carry exchange when a signal is time-chunked over ranks.
+template <class Elem>
+__global__ void __launch_bounds__(32)
+scan_total_kernel(const DevProblem* __restrict__ probs, ScanArgs a, const double* __restrict__ tile_buf,
+                  double* __restrict__ total) {
+  using Map = typename Elem::Map;
+  constexpr int W = Elem::kMapDoubles;
+  const int n = threadIdx.x, M = probs[0].M;
+  if (n >= M) return;
+  const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
+  Map acc, e;
+  Elem::load_map(acc, tile_buf + (size_t)n * W);
+  for (long long t = 1; t < ntiles; ++t) {
+    Elem::load_map(e, tile_buf + ((size_t)t * M + n) * W);
+    Elem::compose(acc, e);
+  }
+  Elem::store_map(acc, total + (size_t)n * W);
 }
 
 template <class Elem>
