@@ -25,7 +25,8 @@ from . import _lib
 
 (ST_RESET, ST_ADF, ST_SUM_LZ, ST_FILTER_REDUCE, ST_FILTER_APPLY, ST_LAST_STEP, ST_COPY_MF, ST_SMOOTHER_REDUCE,
  ST_SMOOTHER_APPLY, ST_SITE_UPDATE, ST_CARRY_MEAN, ST_GET_SITES, ST_SET_SITES, ST_GET_MEAN, ST_SET_MEAN, ST_GET_MCARRY,
- ST_SET_MCARRY, ST_GET_DIAG, ST_RESET_DIAG, ST_GET_VM0, ST_SET_VM0, ST_SET_TRACE, ST_FINISH) = range(23)
+ ST_SET_MCARRY, ST_GET_DIAG, ST_RESET_DIAG, ST_GET_VM0, ST_SET_VM0, ST_SET_TRACE, ST_FINISH, ST_GET_COV,
+ ST_SET_COV) = range(25)
 
 
 def split_ranges(T, world):
@@ -156,12 +157,60 @@ def run_ihgp_chunked(plan, comm, ep_damping):
     return ranges
 
 
+def run_full_chunked(plan, comm, ep_damping):
+    """The same for a KIND_FULL / MODE_PREDICT plan (gf_ep_modulator_nmf.m:113-283): the first filter
+    pass replicated, the parallel Kalman-filter scan, the RTS scan and the site updates sharded.  The
+    full-state filter element of step k uses only the sites of step k, so no site halo is needed; the
+    carries are (A, b, C, eta, J) resp. (E, g, L) per latent block."""
+    mdl = plan.models[0]
+    T, M, n, itts = plan.T, mdl.M, mdl.n, plan.ep_itts
+    BM = {1: 2, 2: 2, 3: 3, 4: 4, 5: 6, 6: 6, 7: 8, 8: 8}[max(mdl.bz, mdl.bg)]
+    Wf, Ws, PB = 3 * BM * BM + 2 * BM, 2 * BM * BM + BM, M * BM * BM
+    rank, world = comm.rank, comm.world
+    ranges = split_ranges(T, world)
+    t0, t1 = ranges[rank]
+    _lib.check(_lib.lib().nsagp_plan_set_range(plan._h, t0, t1))
+    damping = np.atleast_1d(np.asarray(ep_damping, float))
+    last = world - 1
+    _stage(plan, ST_RESET)
+    damp = damping[0]
+    for itt in range(1, itts + 1):
+        _stage(plan, ST_RESET_DIAG)
+        if itt == 1:
+            _stage(plan, ST_ADF, x=damp)
+            _stage(plan, ST_SET_TRACE, x=-_stage(plan, ST_SUM_LZ, k=1, n_out=1)[0], k=0)      # nlZ(1) (:186-188)
+        else:
+            aggs = comm.allgather(_stage(plan, ST_FILTER_REDUCE, n_out=M * Wf))
+            _stage(plan, ST_FILTER_APPLY, inp=np.concatenate(aggs[:rank]) if rank else np.zeros(0))
+            if rank == last:
+                _stage(plan, ST_LAST_STEP, x=damp)
+        if itt == itts:
+            _stage(plan, ST_COPY_MF)
+        if itt < itts:
+            damp = damping[itt]
+        state = comm.allgather(np.concatenate([_stage(plan, ST_GET_MEAN, k=T - 1, n_out=n),
+                                               _stage(plan, ST_GET_COV, k=T - 1, n_out=PB)]))[last]
+        _stage(plan, ST_SET_MEAN, k=T - 1, inp=state[:n])
+        _stage(plan, ST_SET_COV, k=T - 1, inp=state[n:])
+        aggs = comm.allgather(_stage(plan, ST_SMOOTHER_REDUCE, n_out=M * Ws))
+        right = aggs[rank + 1:][::-1]
+        _stage(plan, ST_SMOOTHER_APPLY, inp=np.concatenate(right) if right else np.zeros(0))
+        if itt < itts:
+            _stage(plan, ST_SITE_UPDATE, x=damp)
+            lz = comm.allreduce(_stage(plan, ST_SUM_LZ, k=0, n_out=1), "sum")[0]
+            _stage(plan, ST_SET_TRACE, x=-lz, k=itt)                                          # nlZ(itt+1) (:276-278)
+        bits = _stage(plan, ST_GET_DIAG, n_out=2)
+        _stage(plan, ST_SET_TRACE, k=-1 - (itt - 1), inp=comm.allreduce(bits, "max"))
+    _stage(plan, ST_FINISH)
+    return ranges
+
+
 def gather_outputs(plan, comm, ranges, names=("Eft", "Varft", "lb", "ub")):
     """Assemble the time-indexed outputs from every rank's own range; every rank gets the result."""
     res = plan.fetch(0, tuple(names))
     out = {}
     for nm, a in res.items():
-        if isinstance(a, np.ndarray) and a.ndim == 2 and a.shape[1] == plan.T and nm not in ("Varft",):
+        if isinstance(a, np.ndarray) and a.ndim == 2 and a.shape[1] == plan.T and not (nm == "Varft" and plan.kind == _lib.KIND_IHGP):
             parts = comm.allgather(np.ascontiguousarray(a))
             full = np.empty_like(a)
             for r, (lo, hi) in enumerate(ranges):
