@@ -331,11 +331,19 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
   MomCtaSumAddr<DPT> sum_addr;
   sum_addr.init(s_mom + MomCta<DPT>::kCav, n, D);
   const double* Qn = s_q + n * BM * BM;
-  double A[BM * BM], hv[BM], m[BM], P[BM * BM];
+  double A[BM * BM], hv[BM], hA[BM], m[BM], P[BM * BM];
 #pragma unroll
   for (int i = 0; i < BM * BM; ++i) { A[i] = P_.A[n * BM * BM + i]; P[i] = P_.Pinf[n * BM * BM + i]; }   // :117
 #pragma unroll
-  for (int i = 0; i < BM; ++i) { hv[i] = P_.h[n * BM + i]; m[i] = 0.0; }                                  // :116
+  for (int i = 0; i < BM; ++i) { hv[i] = P_.h[n * BM + i]; hA[i] = P_.hA[n * BM + i]; m[i] = 0.0; }       // :116
+  double hQh = 0.0;
+#pragma unroll
+  for (int i = 0; i < BM; ++i) {
+    double w = 0.0;
+#pragma unroll
+    for (int j2 = 0; j2 < BM; ++j2) w = fma(Qn[i + j2 * BM], hv[j2], w);
+    hQh = fma(hv[i], w, hQh);
+  }
   const int off = P_.off[n];
   const int b = P_.off[n + 1] - off;
 
@@ -387,42 +395,33 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
     const double tt_ld = tt_nx, tn_ld = tn_nx;
     const bool obs = !isnan(y);                          // :135 (uniform over the CTA)
     const bool do_mom = obs && (mom_all || k == T - 1);  // :141
-    // predicted moments of step k, kept apart from the posterior of step k-1
-    double mq[BM], Pq[BM * BM];
-    if (k > 0) {                                         // :129-132
-      double AP[BM * BM], Qr[BM * BM];
-#pragma unroll
-      for (int i = 0; i < BM * BM; ++i) Qr[i] = Qn[i];
-#pragma unroll
-      for (int i = 0; i < BM; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < BM; ++j) s = fma(A[i + j * BM], m[j], s);
-        mq[i] = s;
-      }
-      mat_mul<BM>(A, P, AP);
-      mat_mul_bt_add<BM>(AP, A, Qr, Pq);
-    } else {
-#pragma unroll
-      for (int i = 0; i < BM; ++i) mq[i] = m[i];
-#pragma unroll
-      for (int i = 0; i < BM * BM; ++i) Pq[i] = P[i];
-    }
-    double fmu = 0.0, HPH = 0.0, Wv[BM], hP[BM];
+    // Cavity of step k straight from the posterior of step k-1, in O(b^2): with hA = h A,
+    //   fmu = h A m,   h (A P A' + Q) h' = hA P hA' + h Q h'
+    // so the moment warps can start before the O(b^3) prediction of the covariance, which
+    // this warp then computes while they integrate.
+    double fmu = 0.0, HPH = 0.0;
     if (obs) {
+      if (k > 0) {
+        double v = hQh;
 #pragma unroll
-      for (int i = 0; i < BM; ++i) {
-        fmu = fma(hv[i], mq[i], fmu);
-        double w = 0.0, g = 0.0;
+        for (int i = 0; i < BM; ++i) {
+          fmu = fma(hA[i], m[i], fmu);
+          double w = 0.0;
 #pragma unroll
-        for (int j = 0; j < BM; ++j) {
-          w = fma(Pq[i + j * BM], hv[j], w);             // W = P*H'
-          g = fma(hv[j], Pq[j + i * BM], g);             // H*P
+          for (int j2 = 0; j2 < BM; ++j2) w = fma(P[i + j2 * BM], hA[j2], w);
+          v = fma(hA[i], w, v);
         }
-        Wv[i] = w; hP[i] = g;
-      }
+        HPH = v;
+      } else {
 #pragma unroll
-      for (int i = 0; i < BM; ++i) HPH = fma(hP[i], hv[i], HPH);   // diag(H*P*H')
+        for (int i = 0; i < BM; ++i) {
+          fmu = fma(hv[i], m[i], fmu);
+          double w = 0.0;
+#pragma unroll
+          for (int j2 = 0; j2 < BM; ++j2) w = fma(P[i + j2 * BM], hv[j2], w);
+          HPH = fma(hv[i], w, HPH);
+        }
+      }
       if (do_mom) {
         if (active) {
           s_mom[lane] = fmu; s_mom[32 + lane] = HPH;
@@ -440,6 +439,39 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
       tn_nx = St.tnu[(k + 1) * M + n];
     }
     if (pend) flush(false);
+    // predicted moments of step k (:129-132), kept apart from the posterior of step k-1
+    double mq[BM], Pq[BM * BM], Wv[BM], hP[BM];
+    if (k > 0) {
+      double AP[BM * BM], Qr[BM * BM];
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) Qr[i] = Qn[i];
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j2 = 0; j2 < BM; ++j2) s = fma(A[i + j2 * BM], m[j2], s);
+        mq[i] = s;
+      }
+      mat_mul<BM>(A, P, AP);
+      mat_mul_bt_add<BM>(AP, A, Qr, Pq);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BM; ++i) mq[i] = m[i];
+#pragma unroll
+      for (int i = 0; i < BM * BM; ++i) Pq[i] = P[i];
+    }
+    if (obs) {
+#pragma unroll
+      for (int i = 0; i < BM; ++i) {
+        double w = 0.0, g = 0.0;
+#pragma unroll
+        for (int j2 = 0; j2 < BM; ++j2) {
+          w = fma(Pq[i + j2 * BM], hv[j2], w);           // W = P*H'
+          g = fma(hv[j2], Pq[j2 + i * BM], g);           // H*P
+        }
+        Wv[i] = w; hP[i] = g;
+      }
+    }
     double tt = tt_ld, tn = tn_ld, Zm = 1.0;
     if (obs) {
       if (do_mom) {
