@@ -19,6 +19,7 @@
 //                sequential (ADF) pass where latency per step is what matters.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace nsagp {
 
@@ -60,7 +61,10 @@ __device__ __forceinline__ double pep_const(int kind, double sn2, double alpha) 
 
 // One sigma point.  muz/s2z are read with a stride so the same code serves the
 // warp form (stride 1, broadcast) and the thread form (stride = threads per CTA).
-template <int DP>
+// FAST: the straight-line routines of fastmath.cuh (<= 2 ulp, NaN-propagating variants) instead of
+// the library's exp / log / sqrt / division; the warp form keeps the library versions so that the
+// two sequential-pass implementations stay numerically independent of each other.
+template <int DP, bool FAST = false>
 __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, const MomG& g, int s,
                                           double y, double noise, const double* muz,
                                           const double* s2z, int stride) {
@@ -69,7 +73,7 @@ __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, c
   for (int j = 0; j < kNP; ++j) {
     if (j < p.N) {
       x[j] = g.mu[j] + g.sd[j] * p.xn[j * p.S + s];
-      l[j] = log(1.0 + exp(x[j] - p.shift));       // literal link, not log1p (parity)
+      l[j] = FAST ? softplus_fast(x[j] - p.shift) : log(1.0 + exp(x[j] - p.shift));   // literal link, not log1p (parity)
     } else {
       x[j] = 0.0; l[j] = 0.0;
     }
@@ -82,7 +86,7 @@ __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, c
       double ad = 0.0;
 #pragma unroll
       for (int j = 0; j < kNP; ++j) ad = fma(l[j], p.W[d * kNP + j], ad);
-      if (p.kind == 1) ad = sqrt(ad);
+      if (p.kind == 1) ad = FAST ? sqrt_fast2(ad) : sqrt(ad);
       a[d] = ad;
       vs = fma(ad * ad, s2z[d * stride], vs);
       ms = fma(ad, muz[d * stride], ms);
@@ -91,11 +95,11 @@ __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, c
     }
   }
   const double v = noise + vs;
-  const double rv = 1.0 / v;
-  const double rsd = rsqrt(v);
+  const double rv = FAST ? rcp_fast2(v) : 1.0 / v;
+  const double rsd = FAST ? rsqrt_fast2(v) : rsqrt(v);
   const double res = y - ms;
   const double t = res * rsd;
-  const double pdf = exp(-0.5 * (t * t)) * (rsd * kInvSqrt2Pi);
+  const double pdf = (FAST ? exp_fast(-0.5 * (t * t)) : exp(-0.5 * (t * t))) * (rsd * kInvSqrt2Pi);
   const double wp = p.wn[s] * pdf;
   const double q = res * rv;
   const double c1 = wp * q;
@@ -145,7 +149,7 @@ __device__ __forceinline__ double mom_thread(const MomParams& p, double alpha, d
   MomG g;
   mom_setup_g(g, p, mu + p.D * stride, s2 + p.D * stride, stride);
   const double noise = p.sn2 / alpha;
-  for (int s = 0; s < p.S; ++s) mom_point<DP>(acc, p, g, s, y, noise, mu, s2, stride);
+  for (int s = 0; s < p.S; ++s) mom_point<DP, true>(acc, p, g, s, y, noise, mu, s2, stride);
   const double pep = pep_const(p.kind, p.sn2, alpha);
   const double Z = pep * fmax(acc.Z, kJitter);      // fmax(NaN, jitter) = jitter, as MATLAB max
   const double zp = (1.0 / Z) * pep;
