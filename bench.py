@@ -155,11 +155,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    T_sample, itts = 600, EP_ITTS
+    # The workload is ONE signal per GPU (weak scaling: `gpus` independent signals).  The reference's
+    # loop is serial in time (no parfor, n = 41 matrices too small for BLAS threads), so
+    # one signal can use one host core; `gpus` signals use `gpus` cores.
+    cores = max(1, min(os.cpu_count() or 1, args.gpus))
+    T_sample, itts = 1000, EP_ITTS
     value, per_step = cpu_arm(args.steps, args.warmup, T_sample, itts, cores)
-    sample = ("%d independent clips (one per host core) of T=%d, ep_itts=%d per step; plain-C port of "
-              "matlab/ihgp_ep_modulator_nmf.m (oracle/c/nsagp_oracle.c), model/table setup untimed" % (cores, T_sample, itts))
+    sample = ("%d independent signal(s), one per host core (the reference loop is serial per signal), T=%d of the "
+              "workload's 100000 steps, ep_itts=%d per step; plain-C port of matlab/ihgp_ep_modulator_nmf.m "
+              "(oracle/c/nsagp_oracle.c), model/table setup untimed" % (cores, T_sample, itts))
     line = {"impl": "reference", "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value,
             "unit": "time-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
