@@ -151,6 +151,16 @@ int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_f
  * op: 0 1/x, 1 1/sqrt(x), 2 sqrt(x), 3 exp(x), 4 log(x) for x >= 1, 5 log(1+exp(x)). */
 int nsagp_fastmath_eval(int32_t op, int64_t n, const double* x, double* out);
 
+/* Steady-state tables of the infinite-horizon path built natively on the host
+ * (ihgp_ep_modulator_nmf.m:106-134 PPlist, :150-191 PGlist): per latent block, n_coarse Riccati solutions on
+ * ro = logspace(log10_lo, log10_hi, n_coarse) -- the reference calls dare(A',H',Q,ro) and dare(G',0,QQ); here a
+ * doubling algorithm in long double -- interpolated piecewise linearly in r onto the n_fine-point grid
+ * (apxGrid's non-equispaced branch).  The reference uses (32, 200, -2, 4).  Outputs in the nsagp_tables layout:
+ * r[n_fine], PP (sum over blocks n_fine*b*b), PG (sum over blocks n_fine*2*b*b; may be NULL if !want_smoother).
+ * model.Q must already be symmetrised (:97).  No GPU is needed for this call. */
+int nsagp_ihgp_tables(const nsagp_model* model, int32_t want_smoother, int32_t n_coarse, int32_t n_fine,
+                      double log10_lo, double log10_hi, double* r, double* PP, double* PG);
+
 /* ihgp_ep_modulator_nmf / ihgp_ep_modulator_nmf_constraints
  * (ihgp_ep_modulator_nmf.m:195-526 predict, :533-624 nlZ).  y[T] is `yall` after
  * the merge/sort of train and test inputs (:58-67). */

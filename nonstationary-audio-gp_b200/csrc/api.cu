@@ -939,6 +939,7 @@ int plan_reset(nsagp_plan* pl) {
 #include "api_full.inc"
 #include "api_ekf.inc"
 #include "api_chunk.inc"
+#include "api_tables.inc"
 
 extern "C" {
 

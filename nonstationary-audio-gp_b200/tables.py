@@ -45,9 +45,15 @@ class IhgpTables:
         return pp, pg
 
 
-def build_tables(model, want_smoother=True):
+def build_tables(model, want_smoother=True, native=True):
     """Solve the per-block DAREs and interpolate (``model``: ssmodel.BlockModel,
-    with Q already symmetrised as in ihgp_ep_modulator_nmf.m:97)."""
+    with Q already symmetrised as in ihgp_ep_modulator_nmf.m:97).
+
+    native=True: the library's own host routine (C ABI ``nsagp_ihgp_tables``: doubling algorithm
+    in long double, a few milliseconds).  native=False: the same tables through SciPy's generic
+    Riccati / Lyapunov solvers (what the oracle uses; ~0.3 s) -- kept as the cross-check."""
+    if native:
+        return _build_tables_native(model, want_smoother)
     r = np.logspace(-2, 4, N_FINE)
     ro = np.logspace(-2, 4, N_COARSE)
     U = _linear_interp_matrix(ro, r)
@@ -81,3 +87,29 @@ def build_tables(model, want_smoother=True):
         if want_smoother:
             PG.append(U @ bwd)
     return IhgpTables(r, ro, PP, PG if want_smoother else None)
+
+
+def _build_tables_native(model, want_smoother):
+    import ctypes as C
+
+    from . import _lib
+    arrs = [_lib.as_f64(a) for a in (model.A, model.Q, model.Pinf, model.h)]
+    cm = _lib.Model()
+    cm.D, cm.N, cm.bz, cm.bg = model.D, model.N, model.bz, model.bg
+    cm.A, cm.Q, cm.Pinf, cm.h = [_lib.dptr(a) for a in arrs]
+    sizes = model.block_sizes()
+    r = np.empty(N_FINE)
+    pp = np.empty(N_FINE * int(sum(b * b for b in sizes)))
+    pg = np.empty(2 * pp.size) if want_smoother else None
+    _lib.check(_lib.lib().nsagp_ihgp_tables(C.byref(cm), int(want_smoother), N_COARSE, N_FINE, -2.0, 4.0, _lib.dptr(r),
+                                            _lib.dptr(pp), _lib.dptr(pg) if want_smoother else None))
+    PP, PG, o1, o2 = [], [], 0, 0
+    for b in sizes:
+        PP.append(pp[o1:o1 + N_FINE * b * b].reshape(N_FINE, b * b)); o1 += N_FINE * b * b
+        if want_smoother:
+            PG.append(pg[o2:o2 + N_FINE * 2 * b * b].reshape(N_FINE, 2 * b * b)); o2 += N_FINE * 2 * b * b
+    # the grid the look-up thresholds are derived from is the host's own logspace (bitwise what the
+    # reference's logspace gives); the library's pow()-based copy may differ from it in the last ulp
+    grid = np.logspace(-2, 4, N_FINE)
+    assert np.allclose(r, grid, rtol=1e-14, atol=0)
+    return IhgpTables(grid, np.logspace(-2, 4, N_COARSE), PP, PG if want_smoother else None)
