@@ -184,6 +184,16 @@ int nsagp_ep_full(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep
 int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                 const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
 
+/* Form of the dense RTS pass of nsagp_giekf (gf_giekf_modulator_nmf_constraints.m:221-253):
+ * smoother_form 0 = automatic (the parallel scan over time on the FP64 tensor cores when n <= 80, csrc/ekfscan.cuh),
+ * 1 = sequential in time (one CTA), 2 = scan (error if n > 80).  chunk_len (0 = 64): steps composed per CTA;
+ * chunks_per_segment (0 = 2 x SM count): the scan works through the signal in segments of that many chunks,
+ * which bounds its scratch memory (n^2 doubles per step of a segment).  Process-wide setting. */
+int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_per_segment);
+
+/* Device time of the last nsagp_giekf call on this thread: ms[0] filter passes, ms[1] smoother passes (CUDA events). */
+int nsagp_giekf_timings(double* ms, int32_t n);
+
 /* Batched forms: B independent problems of equal shapes (clips x hyper-parameter
  * grid x finite-difference perturbations; what fminunc does around the nlZ mode,
  * demo_toy_modulators_nmf.m:100-104).  models/liks/tables/outs are arrays of B

@@ -17,6 +17,7 @@
 #include "mombatch.cuh"
 #include "adfcta.cuh"
 #include "ekf.cuh"
+#include "ekfscan.cuh"
 
 using namespace nsagp;
 
@@ -1054,6 +1055,21 @@ static int run_hostbuf(int kind, int32_t B, const nsagp_model* models, const nsa
 int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                 const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
   return giekf_impl(model, W, sigma2, g_iter, l_iter, y, T, mode, out);
+}
+
+int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_per_segment) {
+  if (smoother_form < 0 || smoother_form > 2 || chunk_len < 0 || chunks_per_segment < 0)
+    return fail(NSAGP_ERR_INVALID, "smoother_form must be 0, 1 or 2; chunk_len, chunks_per_segment >= 0");
+  g_giekf_cfg.form = smoother_form;
+  g_giekf_cfg.chunk_len = chunk_len > 0 ? chunk_len : 64;
+  g_giekf_cfg.seg_chunks = chunks_per_segment;
+  return NSAGP_OK;
+}
+
+int nsagp_giekf_timings(double* ms, int32_t n) {
+  if (!ms || n < 2) return fail(NSAGP_ERR_INVALID, "need room for 2 values");
+  ms[0] = g_giekf_ms[0]; ms[1] = g_giekf_ms[1];
+  return NSAGP_OK;
 }
 
 int nsagp_ep_ihgp(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep* ep, const nsagp_tables* tables,
