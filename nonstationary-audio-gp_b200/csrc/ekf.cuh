@@ -11,6 +11,7 @@
 // per step, all cooperative in shared memory).
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace nsagp {
 
@@ -187,6 +188,299 @@ giekf_filter_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
       for (int i = tid; i < n * n; i += nth) dst[i] = P[i];
     }
   }
+  if (energy && tid == 0) { a.edata[0] = bad ? NAN : e_acc; if (bad || isnan(e_acc)) atomicCAS(a.status, 0, 3); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Filter / energy pass, latency-oriented form (the default).  Same arithmetic as giekf_filter_kernel
+// above, reorganised so that one time step costs five CTA barriers:
+//   A  finish the previous step's covariance update P -= (K S) K' tile by tile, store that tile to
+//      PS(:,:,k-1), and predict it in registers (A_i tile A_j' + Q) -- one pass over P instead of three.
+//      With the reference's block sizes (BZ, BG > 0: exact compile-time tile shapes) only the tiles on and
+//      below the block diagonal are computed and mirrored, which keeps P exactly symmetric;
+//   B1 H m per latent; link and its derivative per modulator;   B2 Jacobian row (:497-503), h(m) terms;
+//   C  P*JH' with four threads per row, S and h(m) reduced together;
+//   D  gain, mean update, MS store.
+// exp / log / reciprocal are the straight-line versions of fastmath.cuh (<= 2 ulp).
+constexpr int ekf_round_bm(int b) { return b <= 2 ? 2 : b <= 3 ? 3 : b <= 4 ? 4 : b <= 6 ? 6 : 8; }
+template <int BM> struct EkfF2 { static constexpr int TH = BM <= 4 ? 512 : 256; };   // register budget of the tile pass
+
+// One (block_i, block_j) tile of exact shape NI x NJ (blocks padded to BM in sA / sQ).
+template <int NI, int NJ, int BM>
+__device__ __forceinline__ void ekf_tile(double* P, int n, int oi, int oj, const double* Ai, const double* Aj, const double* Qi,
+                                         const double* Ks, const double* Kv, bool predict, double* store, bool mirror) {
+  double X[NI * NJ];
+#pragma unroll
+  for (int c = 0; c < NJ; ++c)
+#pragma unroll
+    for (int r = 0; r < NI; ++r)
+      X[r + c * NI] = fma(-Ks[oi + r], Kv[oj + c], P[(oi + r) + (oj + c) * n]);      // P - K S K' (iekf_update1.m:117)
+  if (store) {
+#pragma unroll
+    for (int c = 0; c < NJ; ++c)
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        store[(oi + r) + (size_t)(oj + c) * n] = X[r + c * NI];
+        if (mirror) store[(oj + c) + (size_t)(oi + r) * n] = X[r + c * NI];
+      }
+  }
+  if (predict) {
+    double Tm[NI * NJ];
+#pragma unroll
+    for (int c = 0; c < NJ; ++c)
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < NI; ++l) s = fma(Ai[r + l * BM], X[l + c * NI], s);
+        Tm[r + c * NI] = s;
+      }
+#pragma unroll
+    for (int c = 0; c < NJ; ++c)
+#pragma unroll
+      for (int r = 0; r < NI; ++r) {
+        double s = Qi ? Qi[r + c * BM] : 0.0;
+#pragma unroll
+        for (int l = 0; l < NJ; ++l) s = fma(Tm[r + l * NI], Aj[c + l * BM], s);
+        X[r + c * NI] = s;
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < NJ; ++c)
+#pragma unroll
+    for (int r = 0; r < NI; ++r) {
+      P[(oi + r) + (oj + c) * n] = X[r + c * NI];
+      if (mirror) P[(oj + c) + (oi + r) * n] = X[r + c * NI];
+    }
+}
+
+// BZ, BG > 0: the model's exact block sizes (reference kernels: BZ in {2,4,6,8}, BG in {1,2,3,4});
+// BZ = BG = 0: any block sizes <= BM, tiles padded to BM with run-time guards.
+template <int BZ, int BG, int BM>
+__global__ void __launch_bounds__(EkfF2<BM>::TH, 1)
+giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
+  const EkfArgs& a = argv[blockIdx.x];
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+  const int D = a.D, N = a.N, M = a.M, n = a.n;
+  const long long T = a.T;
+  const double sigma2 = a.sigma2;
+  const double* __restrict__ yv = a.y;
+  double* __restrict__ MSg = a.MS;
+  double* __restrict__ PSg = a.PS;
+  extern __shared__ double sm[];
+  double* P = sm;                          // [n*n]
+  double* sA = P + (size_t)n * n;          // [M*BM*BM]
+  double* sQ = sA + M * BM * BM;
+  double* sh = sQ + M * BM * BM;           // [M*BM]
+  double* sW = sh + M * BM;                // [D*N]
+  double* mbuf = sW + D * N;               // [2][n]
+  double* JH = mbuf + 2 * n;               // [n]
+  double* PJ = JH + n;                     // [n]
+  double* Kv = PJ + n;                     // [n]  K
+  double* Ks = Kv + n;                     // [n]  K*S
+  double* red = Ks + n;                    // [2][32]
+  double* fv = red + 64;                   // [M]  H m
+  double* spv = fv + M;                    // [N]  linkf(g)
+  double* dlv = spv + N;                   // [N]  dlinkf(g)
+  __shared__ int s_blk[160];
+  __shared__ int s_off[kMaxSites + 1];
+  __shared__ unsigned short s_pair[(kMaxSites * (kMaxSites + 1)) / 2];
+  for (int i = tid; i < n * n; i += nth) P[i] = a.Pinf[i];                     // :168
+  for (int i = tid; i < M * BM * BM; i += nth) { sA[i] = a.A[i]; sQ[i] = a.Q[i]; }
+  for (int i = tid; i < M * BM; i += nth) sh[i] = a.h[i];
+  for (int i = tid; i < D * N; i += nth) sW[i] = a.W[i];
+  for (int i = tid; i < n; i += nth) { mbuf[i] = a.m_io[i]; Kv[i] = 0.0; Ks[i] = 0.0; }
+  for (int b = tid; b <= M; b += nth) s_off[b] = a.off[b];
+  for (int b = tid; b < M; b += nth)
+    for (int i = a.off[b]; i < a.off[b + 1]; ++i) s_blk[i] = b;
+  // pair list of the exact-shape path: [z,z lower incl. diagonal | g,z | g,g lower incl. diagonal]
+  const int nzz = D * (D + 1) / 2, ngz = N * D, ngg = N * (N + 1) / 2;
+  if (BZ > 0) {
+    for (int p = tid; p < nzz + ngz + ngg; p += nth) {
+      int bi, bj;
+      if (p < nzz) { bi = 0; while ((bi + 1) * (bi + 2) / 2 <= p) ++bi; bj = p - bi * (bi + 1) / 2; }
+      else if (p < nzz + ngz) { const int u = p - nzz; bi = D + u / D; bj = u % D; }
+      else { const int u = p - nzz - ngz; int ii = 0; while ((ii + 1) * (ii + 2) / 2 <= u) ++ii; bi = D + ii; bj = D + u - ii * (ii + 1) / 2; }
+      s_pair[p] = (unsigned short)(bi | (bj << 8));
+    }
+  }
+  __syncthreads();
+  double* m = mbuf;
+  double* m2 = mbuf + n;
+  double e_acc = 0.0;
+  bool bad = false;
+  int my_b = 0, my_o = 0, my_nb = 0;
+  double my_h = 0.0;
+  if (tid < n) { my_b = s_blk[tid]; my_o = s_off[my_b]; my_nb = s_off[my_b + 1] - my_o; my_h = sh[my_b * BM + (tid - my_o)]; }
+  double y_next = yv[0];
+
+  // tile pass: finish the pending update (if any), optionally store to PS(:,:,k-1), optionally predict
+  auto tile_pass = [&](bool predict, double* store) {
+    if (BZ > 0) {
+      for (int p = tid; p < nzz + ngz + ngg; p += nth) {
+        const int pr = s_pair[p], bi = pr & 255, bj = pr >> 8;
+        const int oi = s_off[bi], oj = s_off[bj];
+        const double* Ai = sA + bi * BM * BM;
+        const double* Aj = sA + bj * BM * BM;
+        const double* Qi = (bi == bj) ? sQ + bi * BM * BM : nullptr;
+        if (p < nzz) ekf_tile<(BZ > 0 ? BZ : 1), (BZ > 0 ? BZ : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, predict, store, bi != bj);
+        else if (p < nzz + ngz) ekf_tile<(BG > 0 ? BG : 1), (BZ > 0 ? BZ : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, predict, store, true);
+        else ekf_tile<(BG > 0 ? BG : 1), (BG > 0 ? BG : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, predict, store, bi != bj);
+      }
+    } else {
+      for (int pair = tid; pair < M * M; pair += nth) {
+        const int bi = pair % M, bj = pair / M;
+        const int oi = s_off[bi], ni = s_off[bi + 1] - oi;
+        const int oj = s_off[bj], nj = s_off[bj + 1] - oj;
+        double X[BM * BM];
+#pragma unroll
+        for (int c = 0; c < BM; ++c)
+#pragma unroll
+          for (int r = 0; r < BM; ++r) {
+            double v = 0.0;
+            if (r < ni && c < nj) {
+              v = fma(-Ks[oi + r], Kv[oj + c], P[(oi + r) + (size_t)(oj + c) * n]);
+              if (store) store[(oi + r) + (size_t)(oj + c) * n] = v;
+            }
+            X[r + c * BM] = v;
+          }
+        if (predict) {
+          const double* Ai = sA + bi * BM * BM;
+          const double* Aj = sA + bj * BM * BM;
+          double Tm[BM * BM];
+#pragma unroll
+          for (int c = 0; c < BM; ++c)
+#pragma unroll
+            for (int r = 0; r < BM; ++r) {
+              double s2 = 0.0;
+#pragma unroll
+              for (int l = 0; l < BM; ++l) s2 = fma(Ai[r + l * BM], X[l + c * BM], s2);
+              Tm[r + c * BM] = s2;
+            }
+#pragma unroll
+          for (int c = 0; c < BM; ++c)
+#pragma unroll
+            for (int r = 0; r < BM; ++r) {
+              double s2 = (bi == bj) ? sQ[bi * BM * BM + r + c * BM] : 0.0;
+#pragma unroll
+              for (int l = 0; l < BM; ++l) s2 = fma(Tm[r + l * BM], Aj[c + l * BM], s2);
+              X[r + c * BM] = s2;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < BM; ++c)
+#pragma unroll
+          for (int r = 0; r < BM; ++r)
+            if (r < ni && c < nj) P[(oi + r) + (size_t)(oj + c) * n] = X[r + c * BM];
+      }
+    }
+  };
+
+  for (long long k = 0; k < T; ++k) {
+    const double y = y_next;
+    if (k + 1 < T) y_next = yv[k + 1];
+    // ---- A
+    if (k > 0 || energy) {                                                     // :180-183 / :392-393
+      if (tid < n) {
+        double mv = 0.0;
+        for (int c = 0; c < my_nb; ++c) mv = fma(sA[my_b * BM * BM + (tid - my_o) + c * BM], m[my_o + c], mv);
+        m2[tid] = mv;
+      }
+      tile_pass(true, (!energy && k > 0) ? PSg + (size_t)(k - 1) * n * n : nullptr);
+      double* t = m; m = m2; m2 = t;
+      __syncthreads();
+    }
+    const bool upd = !isnan(y) || energy;                                      // :186
+    double Kr = 0.0, S = 0.0;
+    if (upd) {
+      const int iters = energy ? 1 : l_iter;
+      for (int it = 0; it < iters; ++it) {                                     // iekf_update1.m:110-116
+        // ---- B1: f = H m; link values of the modulators
+        if (tid < M) {
+          const int o = s_off[tid], nb = s_off[tid + 1] - o;
+          double f = 0.0;
+          for (int c = 0; c < nb; ++c) f = fma(sh[tid * BM + c], m[o + c], f);
+          fv[tid] = f;
+          if (tid >= D) {
+            const double eg = exp_fast(f);
+            spv[tid - D] = log_ge1_fast(1.0 + eg);                             // linkf(g) = log(1+exp(g))
+            dlv[tid - D] = eg * rcp_fast(eg + 1.0);                            // dlinkf(g) = exp(g)/(exp(g)+1)
+          }
+        }
+        __syncthreads();
+        // ---- B2: Jacobian row entry of this thread's state (:497-503), h(m) contributions (:490-494)
+        double mu_part = 0.0;
+        if (tid < n) {
+          double jh;
+          if (my_b < D) {
+            double wl = 0.0;
+            for (int j = 0; j < N; ++j) wl = fma(sW[my_b * N + j], spv[j], wl);
+            jh = wl * my_h;
+            if (tid == my_o) mu_part = fv[my_b] * wl;
+          } else {
+            const int j = my_b - D;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int d = 0;
+            for (; d + 3 < D; d += 4) {
+              s0 = fma(fv[d], sW[d * N + j], s0);
+              s1 = fma(fv[d + 1], sW[(d + 1) * N + j], s1);
+              s2 = fma(fv[d + 2], sW[(d + 2) * N + j], s2);
+              s3 = fma(fv[d + 3], sW[(d + 3) * N + j], s3);
+            }
+            for (; d < D; ++d) s0 = fma(fv[d], sW[d * N + j], s0);
+            jh = ((s0 + s1) + (s2 + s3)) * dlv[j] * my_h;
+          }
+          JH[tid] = jh;
+        }
+        __syncthreads();
+        // ---- C: P*JH' (four threads per row), S = R + JH P JH', h(m)
+        double s_part = 0.0;
+        for (int r0 = 0; r0 < n; r0 += nth >> 2) {                               // uniform trip count: shuffles inside
+          const int r = r0 + (tid >> 2);
+          double sa = 0.0, sb = 0.0;
+          if (r < n) {
+            int c = tid & 3;
+            for (; c + 4 < n; c += 8) {
+              sa = fma(P[r + (size_t)c * n], JH[c], sa);
+              sb = fma(P[r + (size_t)(c + 4) * n], JH[c + 4], sb);
+            }
+            if (c < n) sa = fma(P[r + (size_t)c * n], JH[c], sa);
+          }
+          double s = sa + sb;
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if ((tid & 3) == 0 && r < n) { PJ[r] = s; s_part = fma(JH[r], s, s_part); }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
+          mu_part += __shfl_xor_sync(0xffffffffu, mu_part, o);
+        }
+        if (lane == 0) { red[warp] = s_part; red[32 + warp] = mu_part; }
+        __syncthreads();
+        S = sigma2;
+        double MU = 0.0;
+        for (int w = 0; w < nwarps; ++w) { S += red[w]; MU += red[32 + w]; }
+        if (energy) {
+          if (!(S > 0.0)) bad = true;                                          // :417-427 -> NaN energy
+          const double v = y - MU;
+          if (tid == 0) e_acc += 0.5 * log(2.0 * 3.14159265358979323846) + log(sqrt(S)) + 0.5 * v * v / S;
+        }
+        // ---- D
+        if (tid < n) {
+          Kr = PJ[tid] / S;
+          m[tid] = fma(Kr, y - MU, m[tid]);                                    // M = M + K (y - MU)
+        }
+        if (it + 1 < iters) __syncthreads();
+      }
+    }
+    if (tid < n) {
+      Kv[tid] = Kr; Ks[tid] = Kr * S;                                          // consumed by the next tile pass
+      if (!energy) MSg[k * n + tid] = m[tid];                                  // :201
+    }
+    __syncthreads();
+  }
+  if (!energy) tile_pass(false, PSg + (size_t)(T - 1) * n * n);                // last covariance (:202)
   if (energy && tid == 0) { a.edata[0] = bad ? NAN : e_acc; if (bad || isnan(e_acc)) atomicCAS(a.status, 0, 3); }
 }
 
