@@ -184,6 +184,13 @@ int nsagp_ep_full(const nsagp_model* model, const nsagp_lik* lik, const nsagp_ep
 int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                 const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
 
+/* gf_giekf_modulator_nmf (the file without constraints; callers: experiments/missing_data_music.m:128,
+ * noise_reduction_speech.m:97, synthetic_data_experiment.m:176): as nsagp_giekf, but the state (m, P) is
+ * initialised on the first global iteration only (gf_giekf_modulator_nmf.m:127-131), so the smoothed mean AND
+ * covariance of the first time step start the next filter pass. */
+int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
+                      const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
+
 /* Form of the dense RTS pass of nsagp_giekf (gf_giekf_modulator_nmf_constraints.m:221-253):
  * smoother_form 0 = automatic (the parallel scan over time on the FP64 tensor cores when n <= 80, csrc/ekfscan.cuh),
  * 1 = the first-generation kernels (filter and a smoother that is sequential in time; kept as a cross-check),

@@ -14,7 +14,7 @@ from . import _lib, batch, chunked, cubature, ssmodel, synth, tables            
 from ._lib import NsagpError, build                                       # noqa: F401
 from .cubature import gauher, mvhermgauss_unit, utp_ws                    # noqa: F401
 from .entry import (Plan, gf_ep_modulator_nmf, gf_ep_modulator_nmf_constraints,      # noqa: F401
-                    gf_giekf_modulator_nmf_constraints,
+                    gf_giekf_modulator_nmf, gf_giekf_modulator_nmf_constraints,
                     ihgp_ep_modulator_nmf, ihgp_ep_modulator_nmf_constraints,
                     inv_sigmoid, lambda_map, merge_inputs, sigmoid)
 from .lik import Moments, Softplus, likModulatorNMFPower, likModulatorPreCalcwn      # noqa: F401

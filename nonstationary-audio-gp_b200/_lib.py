@@ -111,6 +111,7 @@ def lib():
     L.nsagp_plan_set_adf_form.argtypes = [C.c_void_p, C.c_int]
     L.nsagp_giekf.argtypes = [C.POINTER(Model), c_double_p, C.c_double, C.c_int32, C.c_int32, c_double_p, C.c_int64,
                               C.c_int32, C.POINTER(Outputs)]
+    L.nsagp_giekf_carry.argtypes = L.nsagp_giekf.argtypes
     L.nsagp_giekf_config.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.nsagp_giekf_timings.argtypes = [c_double_p, C.c_int32]
     L.nsagp_plan_set_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
@@ -127,7 +128,7 @@ EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_s
            "nsagp_ep_ihgp_batch", "nsagp_ep_full_batch", "nsagp_plan_create", "nsagp_plan_run",
            "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings", "nsagp_plan_keep_pf",
            "nsagp_plan_set_adf_form", "nsagp_fastmath_eval", "nsagp_release_cache", "nsagp_giekf", "nsagp_plan_set_range",
-           "nsagp_plan_stage", "nsagp_ihgp_tables", "nsagp_giekf_config", "nsagp_giekf_timings"]
+           "nsagp_plan_stage", "nsagp_ihgp_tables", "nsagp_giekf_config", "nsagp_giekf_timings", "nsagp_giekf_carry"]
 
 
 def check(status):

@@ -1054,7 +1054,12 @@ static int run_hostbuf(int kind, int32_t B, const nsagp_model* models, const nsa
 
 int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                 const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
-  return giekf_impl(model, W, sigma2, g_iter, l_iter, y, T, mode, out);
+  return giekf_impl(model, W, sigma2, g_iter, l_iter, 0, y, T, mode, out);
+}
+
+int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
+                      const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
+  return giekf_impl(model, W, sigma2, g_iter, l_iter, 1, y, T, mode, out);
 }
 
 int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_per_segment) {

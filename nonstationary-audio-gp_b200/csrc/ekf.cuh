@@ -29,7 +29,8 @@ struct EkfArgs {
   double sigma2;
   const double* y;               // [T]
   double* MS;                    // [T][n]
-  double* PS;                    // [T][n*n]
+  double* PS;                    // [T][ps_stride], n*n used per step (dense, column-major)
+  long long ps_stride;           // doubles per step: n*n rounded up to even, so that every step is 16-byte aligned (bulk stores)
   double* m_io;                  // [n] mean carried between global iterations (:165-168)
   double* edata;                 // [1] energy (energy mode)
   int* status;
@@ -184,7 +185,7 @@ giekf_filter_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
     }
     if (!energy) {                                                             // :201-203
       for (int i = tid; i < n; i += nth) a.MS[k * n + i] = m[i];
-      double* dst = a.PS + (size_t)k * n * n;
+      double* dst = a.PS + (size_t)k * a.ps_stride;
       for (int i = tid; i < n * n; i += nth) dst[i] = P[i];
     }
   }
@@ -202,89 +203,111 @@ giekf_filter_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
 //   C  P*JH' with four threads per row, S and h(m) reduced together;
 //   D  gain, mean update, MS store.
 // exp / log / reciprocal are the straight-line versions of fastmath.cuh (<= 2 ulp).
-constexpr int ekf_round_bm(int b) { return b <= 2 ? 2 : b <= 3 ? 3 : b <= 4 ? 4 : b <= 6 ? 6 : 8; }
-template <int BM> struct EkfF2 { static constexpr int TH = BM <= 4 ? 512 : 256; };   // register budget of the tile pass
+#ifdef NSAGP_EKF_PROFILE
+// cycles between the barriers of one step, summed in registers and written once at the end
+// (profiles/microbench/ekf_step.cu)
+__device__ long long g_ekf_prof[8];
+#define EKF_CLK(i) do { const long long t_ = clock64(); prof_acc[i] += t_ - t_prev; t_prev = t_; } while (0)
+#define EKF_CLK_AT(i, who) do { if (tid == (who)) prof_acc[i] += clock64() - t_step; } while (0)
+#define EKF_CLK_STEP() const long long t_step = clock64()
+#define EKF_CLK_DECL() long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long t_prev = clock64()
+#define EKF_CLK_FLUSH(nm, nmean, nthr) do { \
+    if (tid == 0) { g_ekf_prof[0] = prof_acc[0]; g_ekf_prof[1] = prof_acc[1]; g_ekf_prof[2] = prof_acc[2]; } \
+    if (tid == (nm)) g_ekf_prof[3] = prof_acc[3]; \
+    if (tid == (nmean)) g_ekf_prof[4] = prof_acc[4]; \
+    if (tid == (nthr)) g_ekf_prof[5] = prof_acc[5]; } while (0)
+#else
+#define EKF_CLK(i) do { } while (0)
+#define EKF_CLK_AT(i, who) do { } while (0)
+#define EKF_CLK_STEP() do { } while (0)
+#define EKF_CLK_DECL() do { } while (0)
+#define EKF_CLK_FLUSH(nm, nmean, nthr) do { } while (0)
+#endif
 
-// One (block_i, block_j) tile of exact shape NI x NJ (blocks padded to BM in sA / sQ).
+constexpr int ekf_round_bm(int b) { return b <= 2 ? 2 : b <= 3 ? 3 : b <= 4 ? 4 : b <= 6 ? 6 : 8; }
+template <int BM> struct EkfF2 { static constexpr int TH = BM <= 3 ? 768 : BM <= 4 ? 512 : 256; };   // register budget of the tile pass
+
+// One (block_i, block_j) tile of exact shape NI x NJ (blocks padded to BM in sA / sQ): finish the pending update,
+// stage the updated tile (and its mirror image) for the bulk store, predict in registers, write back.
 template <int NI, int NJ, int BM>
 __device__ __forceinline__ void ekf_tile(double* P, int n, int oi, int oj, const double* Ai, const double* Aj, const double* Qi,
-                                         const double* Ks, const double* Kv, bool predict, double* store, bool mirror) {
-  double X[NI * NJ];
-#pragma unroll
-  for (int c = 0; c < NJ; ++c)
-#pragma unroll
-    for (int r = 0; r < NI; ++r)
-      X[r + c * NI] = fma(-Ks[oi + r], Kv[oj + c], P[(oi + r) + (oj + c) * n]);      // P - K S K' (iekf_update1.m:117)
-  if (store) {
-#pragma unroll
-    for (int c = 0; c < NJ; ++c)
-#pragma unroll
-      for (int r = 0; r < NI; ++r) {
-        store[(oi + r) + (size_t)(oj + c) * n] = X[r + c * NI];
-        if (mirror) store[(oj + c) + (size_t)(oi + r) * n] = X[r + c * NI];
-      }
-  }
-  if (predict) {
-    double Tm[NI * NJ];
-#pragma unroll
-    for (int c = 0; c < NJ; ++c)
-#pragma unroll
-      for (int r = 0; r < NI; ++r) {
-        double s = 0.0;
-#pragma unroll
-        for (int l = 0; l < NI; ++l) s = fma(Ai[r + l * BM], X[l + c * NI], s);
-        Tm[r + c * NI] = s;
-      }
-#pragma unroll
-    for (int c = 0; c < NJ; ++c)
-#pragma unroll
-      for (int r = 0; r < NI; ++r) {
-        double s = Qi ? Qi[r + c * BM] : 0.0;
-#pragma unroll
-        for (int l = 0; l < NJ; ++l) s = fma(Tm[r + l * NI], Aj[c + l * BM], s);
-        X[r + c * NI] = s;
-      }
-  }
+                                         const double* Ks, const double* Kv, double* Pout, bool mirror) {
+  double X[NI * NJ], Tm[NI * NJ];
 #pragma unroll
   for (int c = 0; c < NJ; ++c)
 #pragma unroll
     for (int r = 0; r < NI; ++r) {
-      P[(oi + r) + (oj + c) * n] = X[r + c * NI];
-      if (mirror) P[(oj + c) + (oi + r) * n] = X[r + c * NI];
+      const double v = fma(-Ks[oi + r], Kv[oj + c], P[(oi + r) + (oj + c) * n]);      // P - K S K' (iekf_update1.m:117)
+      X[r + c * NI] = v;
+      Pout[(oi + r) + (oj + c) * n] = v;
+      if (mirror) Pout[(oj + c) + (oi + r) * n] = v;
+    }
+#pragma unroll
+  for (int c = 0; c < NJ; ++c)
+#pragma unroll
+    for (int r = 0; r < NI; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < NI; ++l) s = fma(Ai[r + l * BM], X[l + c * NI], s);
+      Tm[r + c * NI] = s;
+    }
+#pragma unroll
+  for (int c = 0; c < NJ; ++c)
+#pragma unroll
+    for (int r = 0; r < NI; ++r) {
+      double s = Qi ? Qi[r + c * BM] : 0.0;
+#pragma unroll
+      for (int l = 0; l < NJ; ++l) s = fma(Tm[r + l * NI], Aj[c + l * BM], s);
+      P[(oi + r) + (oj + c) * n] = s;
+      if (mirror) P[(oj + c) + (oi + r) * n] = s;
     }
 }
 
-// BZ, BG > 0: the model's exact block sizes (reference kernels: BZ in {2,4,6,8}, BG in {1,2,3,4});
-// BZ = BG = 0: any block sizes <= BM, tiles padded to BM with run-time guards.
+// BZ, BG > 0: the model's exact block sizes (reference kernels: BZ in {2,4,6,8}, BG in {1,2,3,4}); the updated
+// covariance of each step is staged in shared memory and leaves through one bulk copy (cp.async.bulk, the TMA
+// engine) per step -- 5 000 scattered 8-byte stores per step from one SM were the slowest part of the step.
+// BZ = BG = 0: any block sizes <= BM, tiles padded to BM with run-time guards, direct stores (also the route for
+// states too large for the staging buffer).
+// Warp roles: warps [0, NMW) ("mean group", NMW = ceil(max(n, M) / 32)) predict the mean and evaluate the
+// Jacobian row from it (phases B1, B2; they synchronise among themselves on named barrier 1) WHILE the
+// other warps run the tile pass -- the Jacobian needs the predicted mean only, not the predicted covariance.
+// The loop body is kept small (single call sites, < 32 KB of SASS): one CTA running alone streams its
+// instructions through a 32 KB L1.5 instruction cache, and a larger body made every phase 3-5x slower.
 template <int BZ, int BG, int BM>
 __global__ void __launch_bounds__(EkfF2<BM>::TH, 1)
 giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
+  constexpr bool kStaged = BZ > 0;
   const EkfArgs& a = argv[blockIdx.x];
-  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int D = a.D, N = a.N, M = a.M, n = a.n;
-  const long long T = a.T;
+  const long long T = a.T, ps_stride = a.ps_stride;
   const double sigma2 = a.sigma2;
   const double* __restrict__ yv = a.y;
   double* __restrict__ MSg = a.MS;
   double* __restrict__ PSg = a.PS;
-  extern __shared__ double sm[];
-  double* P = sm;                          // [n*n]
-  double* sA = P + (size_t)n * n;          // [M*BM*BM]
+  extern __shared__ __align__(16) double sm[];
+  double* Pstage = sm;                       // [ps_stride] (kStaged only) 16-byte aligned source of the bulk store
+  double* P = sm + (kStaged ? ps_stride : 0); // [n*n]
+  double* sA = P + (size_t)n * n;            // [M*BM*BM]
   double* sQ = sA + M * BM * BM;
-  double* sh = sQ + M * BM * BM;           // [M*BM]
-  double* sW = sh + M * BM;                // [D*N]
-  double* mbuf = sW + D * N;               // [2][n]
-  double* JH = mbuf + 2 * n;               // [n]
-  double* PJ = JH + n;                     // [n]
-  double* Kv = PJ + n;                     // [n]  K
-  double* Ks = Kv + n;                     // [n]  K*S
-  double* red = Ks + n;                    // [2][32]
-  double* fv = red + 64;                   // [M]  H m
-  double* spv = fv + M;                    // [N]  linkf(g)
-  double* dlv = spv + N;                   // [N]  dlinkf(g)
+  double* sh = sQ + M * BM * BM;             // [M*BM]
+  double* sW = sh + M * BM;                  // [D*N]
+  double* mbuf = sW + D * N;                 // [2][n]
+  double* JH = mbuf + 2 * n;                 // [n]
+  double* PJ = JH + n;                       // [n]
+  double* Kv = PJ + n;                       // [n]  K
+  double* Ks = Kv + n;                       // [n]  K*S
+  double* red = Ks + n;                      // [2][32]
+  double* fv = red + 64;                     // [M]  H m
+  double* spv = fv + M;                      // [N]  linkf(g)
+  double* dlv = spv + N;                     // [N]  dlinkf(g)
+  double* sS = dlv + N;                      // [2]  S, y - h(m)
+  double* zWv = sS + 2;                      // [N]  z'W
+  double* mup = zWv + N;                     // [D]  terms of h(m)
   __shared__ int s_blk[160];
   __shared__ int s_off[kMaxSites + 1];
-  __shared__ unsigned short s_pair[(kMaxSites * (kMaxSites + 1)) / 2];
+  __shared__ unsigned short s_pair[(kMaxSites * (kMaxSites + 1)) / 2 + 96];
+  if (kStaged) for (int i = tid; i < ps_stride; i += nth) Pstage[i] = 0.0;
   for (int i = tid; i < n * n; i += nth) P[i] = a.Pinf[i];                     // :168
   for (int i = tid; i < M * BM * BM; i += nth) { sA[i] = a.A[i]; sQ[i] = a.Q[i]; }
   for (int i = tid; i < M * BM; i += nth) sh[i] = a.h[i];
@@ -293,18 +316,26 @@ giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
   for (int b = tid; b <= M; b += nth) s_off[b] = a.off[b];
   for (int b = tid; b < M; b += nth)
     for (int i = a.off[b]; i < a.off[b + 1]; ++i) s_blk[i] = b;
-  // pair list of the exact-shape path: [z,z lower incl. diagonal | g,z | g,g lower incl. diagonal]
+  // pair list of the exact-shape path: [g,g lower incl. diagonal | g,z | z,z lower incl. diagonal], every class
+  // starting at a multiple of 32 so that no warp mixes tile shapes (0xffff = padding entry)
   const int nzz = D * (D + 1) / 2, ngz = N * D, ngg = N * (N + 1) / 2;
+  const int o_gz = (ngg + 31) & ~31, o_zz = o_gz + ((ngz + 31) & ~31);
+  const int npairs = BZ > 0 ? o_zz + nzz : M * M;
   if (BZ > 0) {
-    for (int p = tid; p < nzz + ngz + ngg; p += nth) {
-      int bi, bj;
-      if (p < nzz) { bi = 0; while ((bi + 1) * (bi + 2) / 2 <= p) ++bi; bj = p - bi * (bi + 1) / 2; }
-      else if (p < nzz + ngz) { const int u = p - nzz; bi = D + u / D; bj = u % D; }
-      else { const int u = p - nzz - ngz; int ii = 0; while ((ii + 1) * (ii + 2) / 2 <= u) ++ii; bi = D + ii; bj = D + u - ii * (ii + 1) / 2; }
+    for (int p = tid; p < npairs; p += nth) {
+      int bi = 255, bj = 255;
+      if (p < ngg) { int ii = 0; while ((ii + 1) * (ii + 2) / 2 <= p) ++ii; bi = D + ii; bj = D + p - ii * (ii + 1) / 2; }
+      else if (p >= o_gz && p < o_gz + ngz) { const int u = p - o_gz; bi = D + u / D; bj = u % D; }
+      else if (p >= o_zz) { const int u = p - o_zz; bi = 0; while ((bi + 1) * (bi + 2) / 2 <= u) ++bi; bj = u - bi * (bi + 1) / 2; }
       s_pair[p] = (unsigned short)(bi | (bj << 8));
     }
   }
   __syncthreads();
+  const int NMW = max(2, (max(n, M) + 31) >> 5);       // warps of the mean group
+  const int n_mean = NMW * 32;
+  const bool mean_grp = warp < NMW;
+  const int t_idx = tid - n_mean, t_cnt = nth - n_mean; // tile-pass thread index / count
+  const int issuer = n_mean;                            // first thread of the tile warps issues the bulk stores
   double* m = mbuf;
   double* m2 = mbuf + n;
   double e_acc = 0.0;
@@ -313,175 +344,220 @@ giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
   double my_h = 0.0;
   if (tid < n) { my_b = s_blk[tid]; my_o = s_off[my_b]; my_nb = s_off[my_b + 1] - my_o; my_h = sh[my_b * BM + (tid - my_o)]; }
   double y_next = yv[0];
+  EKF_CLK_DECL();
+  auto bar_mean = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_mean) : "memory"); };
 
-  // tile pass: finish the pending update (if any), optionally store to PS(:,:,k-1), optionally predict
-  auto tile_pass = [&](bool predict, double* store) {
-    if (BZ > 0) {
-      for (int p = tid; p < nzz + ngz + ngg; p += nth) {
-        const int pr = s_pair[p], bi = pr & 255, bj = pr >> 8;
-        const int oi = s_off[bi], oj = s_off[bj];
-        const double* Ai = sA + bi * BM * BM;
-        const double* Aj = sA + bj * BM * BM;
-        const double* Qi = (bi == bj) ? sQ + bi * BM * BM : nullptr;
-        if (p < nzz) ekf_tile<(BZ > 0 ? BZ : 1), (BZ > 0 ? BZ : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, predict, store, bi != bj);
-        else if (p < nzz + ngz) ekf_tile<(BG > 0 ? BG : 1), (BZ > 0 ? BZ : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, predict, store, true);
-        else ekf_tile<(BG > 0 ? BG : 1), (BG > 0 ? BG : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, predict, store, bi != bj);
-      }
-    } else {
-      for (int pair = tid; pair < M * M; pair += nth) {
-        const int bi = pair % M, bj = pair / M;
-        const int oi = s_off[bi], ni = s_off[bi + 1] - oi;
-        const int oj = s_off[bj], nj = s_off[bj + 1] - oj;
-        double X[BM * BM];
-#pragma unroll
-        for (int c = 0; c < BM; ++c)
-#pragma unroll
-          for (int r = 0; r < BM; ++r) {
-            double v = 0.0;
-            if (r < ni && c < nj) {
-              v = fma(-Ks[oi + r], Kv[oj + c], P[(oi + r) + (size_t)(oj + c) * n]);
-              if (store) store[(oi + r) + (size_t)(oj + c) * n] = v;
-            }
-            X[r + c * BM] = v;
-          }
-        if (predict) {
-          const double* Ai = sA + bi * BM * BM;
-          const double* Aj = sA + bj * BM * BM;
-          double Tm[BM * BM];
-#pragma unroll
-          for (int c = 0; c < BM; ++c)
-#pragma unroll
-            for (int r = 0; r < BM; ++r) {
-              double s2 = 0.0;
-#pragma unroll
-              for (int l = 0; l < BM; ++l) s2 = fma(Ai[r + l * BM], X[l + c * BM], s2);
-              Tm[r + c * BM] = s2;
-            }
-#pragma unroll
-          for (int c = 0; c < BM; ++c)
-#pragma unroll
-            for (int r = 0; r < BM; ++r) {
-              double s2 = (bi == bj) ? sQ[bi * BM * BM + r + c * BM] : 0.0;
-#pragma unroll
-              for (int l = 0; l < BM; ++l) s2 = fma(Tm[r + l * BM], Aj[c + l * BM], s2);
-              X[r + c * BM] = s2;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < BM; ++c)
-#pragma unroll
-          for (int r = 0; r < BM; ++r)
-            if (r < ni && c < nj) P[(oi + r) + (size_t)(oj + c) * n] = X[r + c * BM];
-      }
-    }
-  };
-
-  for (long long k = 0; k < T; ++k) {
-    const double y = y_next;
+  // Step k = T is the flush of the last covariance (:202): tile pass + store only (predict mode).
+  for (long long k = 0; k <= T; ++k) {
+    const bool last = k == T;
+    if (last && energy) break;
+    const double y = last ? NAN : y_next;
     if (k + 1 < T) y_next = yv[k + 1];
-    // ---- A
-    if (k > 0 || energy) {                                                     // :180-183 / :392-393
-      if (tid < n) {
-        double mv = 0.0;
-        for (int c = 0; c < my_nb; ++c) mv = fma(sA[my_b * BM * BM + (tid - my_o) + c * BM], m[my_o + c], mv);
-        m2[tid] = mv;
-      }
-      tile_pass(true, (!energy && k > 0) ? PSg + (size_t)(k - 1) * n * n : nullptr);
-      double* t = m; m = m2; m2 = t;
-      __syncthreads();
-    }
-    const bool upd = !isnan(y) || energy;                                      // :186
-    double Kr = 0.0, S = 0.0;
-    if (upd) {
-      const int iters = energy ? 1 : l_iter;
-      for (int it = 0; it < iters; ++it) {                                     // iekf_update1.m:110-116
-        // ---- B1: f = H m; link values of the modulators
+    const bool do_pred = k > 0 || energy;                                      // :180-183 / :392-393
+    const bool upd = !last && (!isnan(y) || energy);                           // :186
+    const bool st = !energy && k > 0;                                          // PS(:,:,k-1) leaves in this step
+    const int iters = upd ? (energy ? 1 : l_iter) : 0;
+    double mu_part = 0.0, Kr = 0.0, S = 0.0;
+    EKF_CLK_STEP();
+    for (int it = 0; it < max(iters, 1); ++it) {                               // iekf_update1.m:110-116
+      // ---- A (tile warps, first iteration)  ||  mean prediction, B1, B2 (mean group)
+      if (mean_grp) {
+        const bool pred_now = it == 0 && do_pred && !last;
+        const double* mc = pred_now ? m2 : m;
+        if (it > 0) bar_mean();                                                // phase D's mean is complete
+        // B1: every latent's thread predicts its own block of the mean, f = H m; warp 0 reduces z'W over the
+        // subbands; the modulators' threads evaluate the link and its derivative
+        double f = 0.0;
         if (tid < M) {
           const int o = s_off[tid], nb = s_off[tid + 1] - o;
-          double f = 0.0;
-          for (int c = 0; c < nb; ++c) f = fma(sh[tid * BM + c], m[o + c], f);
+          if (pred_now) {
+            for (int r = 0; r < nb; ++r) {
+              double mv = 0.0;
+              for (int c = 0; c < nb; ++c) mv = fma(sA[tid * BM * BM + r + c * BM], m[o + c], mv);
+              m2[o + r] = mv;
+              f = fma(sh[tid * BM + r], mv, f);
+            }
+          } else if (upd) {
+            for (int c = 0; c < nb; ++c) f = fma(sh[tid * BM + c], mc[o + c], f);
+          }
           fv[tid] = f;
-          if (tid >= D) {
+        }
+        if (upd) {
+          if (warp == 0) {
+            double f2 = 0.0;                                                   // subband lane + 32 (D <= 64)
+            const int d2 = lane + 32;
+            if (d2 < D) {
+              const int o = s_off[d2], nb = s_off[d2 + 1] - o;
+              for (int r = 0; r < nb; ++r) {
+                double mv = 0.0;
+                if (pred_now) { for (int c = 0; c < nb; ++c) mv = fma(sA[d2 * BM * BM + r + c * BM], m[o + c], mv); }
+                else mv = mc[o + r];
+                f2 = fma(sh[d2 * BM + r], mv, f2);
+              }
+            }
+            const double f1 = lane < D ? f : 0.0;
+            for (int j = 0; j < N; ++j) {
+              double zw = lane < D ? f1 * sW[lane * N + j] : 0.0;
+              if (d2 < D) zw = fma(f2, sW[d2 * N + j], zw);
+#pragma unroll
+              for (int o = 16; o >= 1; o >>= 1) zw += __shfl_xor_sync(0xffffffffu, zw, o);
+              if (lane == 0) zWv[j] = zw;
+            }
+          }
+          if (tid >= D && tid < M) {
             const double eg = exp_fast(f);
             spv[tid - D] = log_ge1_fast(1.0 + eg);                             // linkf(g) = log(1+exp(g))
             dlv[tid - D] = eg * rcp_fast(eg + 1.0);                            // dlinkf(g) = exp(g)/(exp(g)+1)
           }
-        }
-        __syncthreads();
-        // ---- B2: Jacobian row entry of this thread's state (:497-503), h(m) contributions (:490-494)
-        double mu_part = 0.0;
-        if (tid < n) {
-          double jh;
-          if (my_b < D) {
-            double wl = 0.0;
-            for (int j = 0; j < N; ++j) wl = fma(sW[my_b * N + j], spv[j], wl);
-            jh = wl * my_h;
-            if (tid == my_o) mu_part = fv[my_b] * wl;
-          } else {
-            const int j = my_b - D;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int d = 0;
-            for (; d + 3 < D; d += 4) {
-              s0 = fma(fv[d], sW[d * N + j], s0);
-              s1 = fma(fv[d + 1], sW[(d + 1) * N + j], s1);
-              s2 = fma(fv[d + 2], sW[(d + 2) * N + j], s2);
-              s3 = fma(fv[d + 3], sW[(d + 3) * N + j], s3);
+          bar_mean();
+          // B2: Jacobian row entry of this thread's state (:497-503), terms of h(m) (:490-494)
+          if (tid < n) {
+            double jh;
+            if (my_b < D) {
+              double wl = 0.0;
+              for (int j = 0; j < N; ++j) wl = fma(sW[my_b * N + j], spv[j], wl);
+              jh = wl * my_h;
+              if (tid == my_o) mup[my_b] = fv[my_b] * wl;
+            } else {
+              jh = zWv[my_b - D] * dlv[my_b - D] * my_h;
             }
-            for (; d < D; ++d) s0 = fma(fv[d], sW[d * N + j], s0);
-            jh = ((s0 + s1) + (s2 + s3)) * dlv[j] * my_h;
+            JH[tid] = jh;
           }
-          JH[tid] = jh;
+        } else if (pred_now) {
+          bar_mean();
         }
-        __syncthreads();
-        // ---- C: P*JH' (four threads per row), S = R + JH P JH', h(m)
-        double s_part = 0.0;
-        for (int r0 = 0; r0 < n; r0 += nth >> 2) {                               // uniform trip count: shuffles inside
-          const int r = r0 + (tid >> 2);
-          double sa = 0.0, sb = 0.0;
-          if (r < n) {
-            int c = tid & 3;
-            for (; c + 4 < n; c += 8) {
-              sa = fma(P[r + (size_t)c * n], JH[c], sa);
-              sb = fma(P[r + (size_t)(c + 4) * n], JH[c + 4], sb);
-            }
-            if (c < n) sa = fma(P[r + (size_t)c * n], JH[c], sa);
+        EKF_CLK_AT(3, n - 1);
+      } else if (it == 0 && do_pred) {
+        double* store = PSg + (size_t)(st ? k - 1 : 0) * ps_stride;
+        if (BZ > 0) {
+#pragma unroll 1
+          for (int p = t_idx; p < npairs; p += t_cnt) {
+            const int pr = s_pair[p], bi = pr & 255, bj = pr >> 8;
+            if (bi == 255) continue;
+            const int oi = s_off[bi], oj = s_off[bj];
+            const double* Ai = sA + bi * BM * BM;
+            const double* Aj = sA + bj * BM * BM;
+            const double* Qi = (bi == bj) ? sQ + bi * BM * BM : nullptr;
+            if (p < o_gz) ekf_tile<(BG > 0 ? BG : 1), (BG > 0 ? BG : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, Pstage, bi != bj);
+            else if (p < o_zz) ekf_tile<(BG > 0 ? BG : 1), (BZ > 0 ? BZ : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, Pstage, true);
+            else ekf_tile<(BZ > 0 ? BZ : 1), (BZ > 0 ? BZ : 1), BM>(P, n, oi, oj, Ai, Aj, Qi, Ks, Kv, Pstage, bi != bj);
           }
-          double s = sa + sb;
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          if ((tid & 3) == 0 && r < n) { PJ[r] = s; s_part = fma(JH[r], s, s_part); }
-        }
+          if (st) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tiles -> visible to the copy engine
+        } else {
+#pragma unroll 1
+          for (int pair = t_idx; pair < npairs; pair += t_cnt) {
+            const int bi = pair % M, bj = pair / M;
+            const int oi = s_off[bi], ni = s_off[bi + 1] - oi;
+            const int oj = s_off[bj], nj = s_off[bj + 1] - oj;
+            const double* Ai = sA + bi * BM * BM;
+            const double* Aj = sA + bj * BM * BM;
+            double X[BM * BM], Tm[BM * BM];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          s_part += __shfl_xor_sync(0xffffffffu, s_part, o);
-          mu_part += __shfl_xor_sync(0xffffffffu, mu_part, o);
+            for (int c = 0; c < BM; ++c)
+#pragma unroll
+              for (int r = 0; r < BM; ++r) {
+                double v = 0.0;
+                if (r < ni && c < nj) {
+                  v = fma(-Ks[oi + r], Kv[oj + c], P[(oi + r) + (size_t)(oj + c) * n]);
+                  if (st) store[(oi + r) + (size_t)(oj + c) * n] = v;
+                }
+                X[r + c * BM] = v;
+              }
+#pragma unroll
+            for (int c = 0; c < BM; ++c)
+#pragma unroll
+              for (int r = 0; r < BM; ++r) {
+                double s2 = 0.0;
+#pragma unroll
+                for (int l = 0; l < BM; ++l) s2 = fma(Ai[r + l * BM], X[l + c * BM], s2);
+                Tm[r + c * BM] = s2;
+              }
+#pragma unroll
+            for (int c = 0; c < BM; ++c)
+#pragma unroll
+              for (int r = 0; r < BM; ++r) {
+                double s2 = (bi == bj) ? sQ[bi * BM * BM + r + c * BM] : 0.0;
+#pragma unroll
+                for (int l = 0; l < BM; ++l) s2 = fma(Tm[r + l * BM], Aj[c + l * BM], s2);
+                if (r < ni && c < nj) P[(oi + r) + (size_t)(oj + c) * n] = s2;
+              }
+          }
         }
-        if (lane == 0) { red[warp] = s_part; red[32 + warp] = mu_part; }
-        __syncthreads();
-        S = sigma2;
-        double MU = 0.0;
-        for (int w = 0; w < nwarps; ++w) { S += red[w]; MU += red[32 + w]; }
+        EKF_CLK_AT(4, n_mean);
+        EKF_CLK_AT(5, nth - 1);
+      }
+      if (it == 0 && do_pred && !last) { double* t = m; m = m2; m2 = t; }
+      __syncthreads();
+      if (kStaged && it == 0 && st && tid == issuer) {                         // one bulk copy of the staged covariance
+        const unsigned src = (unsigned)__cvta_generic_to_shared(Pstage);
+        double* dst = PSg + (size_t)(k - 1) * ps_stride;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"((unsigned)(ps_stride * 8)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      EKF_CLK(0);
+      if (!upd) break;
+      // ---- C: P*JH' (eight lanes per row)
+      for (int r0 = 0; r0 < n; r0 += nth >> 3) {                               // uniform trip count: shuffles inside
+        const int r = r0 + (tid >> 3);
+        double sa = 0.0, sb = 0.0;
+        if (r < n) {
+          int c = tid & 7;
+#pragma unroll 1
+          for (; c + 8 < n; c += 16) {
+            sa = fma(P[r + (size_t)c * n], JH[c], sa);
+            sb = fma(P[r + (size_t)(c + 8) * n], JH[c + 8], sb);
+          }
+          if (c < n) sa = fma(P[r + (size_t)c * n], JH[c], sa);
+        }
+        double sv = sa + sb;
+        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+        sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+        sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+        if ((tid & 7) == 0 && r < n) PJ[r] = sv;
+      }
+      __syncthreads();
+      EKF_CLK(1);
+      // ---- D (mean group only; the tile warps go straight to the barrier that ends the step)
+      if (mean_grp) {
+        if (warp == 0) {                                                       // S = R + JH P JH' (:S), MU = h(m)
+          double sv = 0.0, mv = 0.0;
+          for (int r = lane; r < n; r += 32) sv = fma(JH[r], PJ[r], sv);
+          for (int d = lane; d < D; d += 32) mv += mup[d];
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            mv += __shfl_xor_sync(0xffffffffu, mv, o);
+          }
+          if (lane == 0) { sS[0] = sigma2 + sv; sS[1] = y - mv; }
+        }
+        bar_mean();
+        S = sS[0];
+        const double v = sS[1];
         if (energy) {
           if (!(S > 0.0)) bad = true;                                          // :417-427 -> NaN energy
-          const double v = y - MU;
           if (tid == 0) e_acc += 0.5 * log(2.0 * 3.14159265358979323846) + log(sqrt(S)) + 0.5 * v * v / S;
         }
-        // ---- D
         if (tid < n) {
-          Kr = PJ[tid] / S;
-          m[tid] = fma(Kr, y - MU, m[tid]);                                    // M = M + K (y - MU)
+          Kr = PJ[tid] * rcp_fast(S);                                          // K = P JH' / S
+          m[tid] = fma(Kr, v, m[tid]);                                         // M = M + K (y - MU)
         }
-        if (it + 1 < iters) __syncthreads();
       }
     }
+    if (last) break;
     if (tid < n) {
       Kv[tid] = Kr; Ks[tid] = Kr * S;                                          // consumed by the next tile pass
       if (!energy) MSg[k * n + tid] = m[tid];                                  // :201
     }
+    if (kStaged && st && tid == issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer reusable
     __syncthreads();
+    EKF_CLK(2);
   }
-  if (!energy) tile_pass(false, PSg + (size_t)(T - 1) * n * n);                // last covariance (:202)
-  if (energy && tid == 0) { a.edata[0] = bad ? NAN : e_acc; if (bad || isnan(e_acc)) atomicCAS(a.status, 0, 3); }
+  if (kStaged && !energy && tid == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  EKF_CLK_FLUSH(n - 1, n_mean, nth - 1);
+  if (energy && tid == 0) {                                                    // thread 0 is in the mean group, which tracks `bad`
+    a.edata[0] = bad ? NAN : e_acc;
+    if (bad || isnan(e_acc)) atomicCAS(a.status, 0, 3);
+  }
 }
 
 // C (n-by-n) = op(X) * op(Y) helpers on shared-memory matrices, all threads cooperate.
@@ -530,7 +606,7 @@ giekf_smoother_kernel(const EkfArgs* __restrict__ argv, const double* __restrict
     for (int i = a.off[b]; i < a.off[b + 1]; ++i) s_blk[i] = b;
   const long long T = a.T;
   for (int i = tid; i < n; i += nth) ms[i] = a.MS[(T - 1) * n + i];
-  for (size_t i = tid; i < nn; i += nth) Ps[i] = a.PS[(size_t)(T - 1) * nn + i];
+  for (size_t i = tid; i < nn; i += nth) Ps[i] = a.PS[(size_t)(T - 1) * a.ps_stride + i];
   if (tid == 0) s_fail = 0;
   __syncthreads();
   double md = 0.0;
@@ -553,7 +629,7 @@ giekf_smoother_kernel(const EkfArgs* __restrict__ argv, const double* __restrict
   emit(T - 1);
   for (long long k = T - 2; k >= 0; --k) {
     for (int i = tid; i < n; i += nth) mk[i] = a.MS[k * n + i];
-    for (size_t i = tid; i < nn; i += nth) { const double v = a.PS[(size_t)k * nn + i]; Pk[i] = v; Pp[i] = v; }
+    for (size_t i = tid; i < nn; i += nth) { const double v = a.PS[(size_t)k * a.ps_stride + i]; Pk[i] = v; Pp[i] = v; }
     __syncthreads();
     ekf_predict_cov<BM>(Pp, a, sA, sQ);                                         // PSkp = A PSk A' + Q (:229)
     // T1 = PSk * A'  (block-diagonal A: column block j of T1 = PSk(:, block j) * A_j')
@@ -622,7 +698,7 @@ giekf_smoother_kernel(const EkfArgs* __restrict__ argv, const double* __restrict
     for (size_t i = tid; i < nn; i += nth) Ps[i] += Pk[i];
     __syncthreads();
     for (int i = tid; i < n; i += nth) a.MS[k * n + i] = ms[i];                 // :249
-    for (size_t i = tid; i < nn; i += nth) a.PS[(size_t)k * nn + i] = Ps[i];
+    for (size_t i = tid; i < nn; i += nth) a.PS[(size_t)k * a.ps_stride + i] = Ps[i];
     emit(k);
     __syncthreads();
   }

@@ -206,7 +206,7 @@ ds_elements_kernel(const __grid_constant__ DsArgs g) {
 
   for (long long k = g.seg_k0 + blockIdx.x; k < g.seg_k1; k += gridDim.x) {
     __syncthreads();
-    ds_load<NP>(Pm, a.PS + (size_t)k * nn, n);
+    ds_load<NP>(Pm, a.PS + (size_t)k * a.ps_stride, n);
     for (int i = tid; i < NP; i += nth) mf[i] = (i < n) ? a.MS[k * n + i] : 0.0;
     // padding of X (zero) and of PSkp (identity)
     for (int i = tid; i < NP * NP; i += nth) {
@@ -310,7 +310,7 @@ ds_elements_kernel(const __grid_constant__ DsArgs g) {
     // here: Cm lower tiles = C (diagonal tiles represented by Dinv), Xm = Y = C^-1 A PS_k.
     // L = PS_k - Y'Y  (= PS_k - G PSkp G'), written over PS_k in HBM.
     {
-      double* Lg = a.PS + (size_t)k * nn;
+      double* Lg = a.PS + (size_t)k * a.ps_stride;
       ds_gemm<NP, true, false>(Xm, Xm, 0, NP / 4, [&](int r, int c, double v0, double v1) {
         if (r < n) {
           if (c < n) Lg[r + (size_t)c * n] = Pm[r + c * LD] - v0;
@@ -385,7 +385,7 @@ ds_compose_kernel(const __grid_constant__ DsArgs g) {
     {
       const long long s = s1 - 1;
       ds_load<NP>(Gm, g.Gt + (size_t)s * nn, n);
-      ds_load<NP>(La, g.ekf.PS + (size_t)(g.seg_k0 + s) * nn, n);
+      ds_load<NP>(La, g.ekf.PS + (size_t)(g.seg_k0 + s) * g.ekf.ps_stride, n);
       for (int i = tid; i < NP; i += nth) ga[i] = (i < n) ? g.gv[s * n + i] : 0.0;
       __syncthreads();
       for (int i = tid; i < NP * NP; i += nth) { const int r = i % NP, c = i / NP; Ea[r + c * LD] = Gm[c + r * LD]; }
@@ -403,7 +403,7 @@ ds_compose_kernel(const __grid_constant__ DsArgs g) {
       __syncthreads();
       // La = T1 G' + L_k
       {
-        const double* Lg = g.ekf.PS + (size_t)(g.seg_k0 + s) * nn;
+        const double* Lg = g.ekf.PS + (size_t)(g.seg_k0 + s) * g.ekf.ps_stride;
         ds_gemm<NP, false, false>(T1, Gm, 0, NP / 4, [&](int r, int c, double v0, double v1) {
           const bool rr = r < n;
           La[r + c * LD] = (rr && c < n) ? v0 + Lg[r + (size_t)c * n] : 0.0;
@@ -535,7 +535,7 @@ ds_apply_kernel(const __grid_constant__ DsArgs g) {
       ds_matvec<NP, true>(Gm, ms, gk, mt, n);
       __syncthreads();
       {
-        double* Pg = g.ekf.PS + (size_t)k * nn;            // holds L_k, receives the smoothed covariance (:249)
+        double* Pg = g.ekf.PS + (size_t)k * g.ekf.ps_stride;            // holds L_k, receives the smoothed covariance (:249)
         ds_gemm<NP, false, false>(T1, Gm, 0, NP / 4, [&](int r, int c, double v0, double v1) {
           const bool rr = r < n;
           double w0 = 0.0, w1 = 0.0;

@@ -309,6 +309,14 @@ def ihgp_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, nu
                 nlz_mode=_lib.MODE_NLZ_RUNNING, adf_form=adf_form)
 
 
+def gf_giekf_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter,
+                           nargout=6, debug_cov=False):
+    """Drop-in for matlab/gf_giekf_modulator_nmf.m (GradObj = 'off'): log-scale parameter vector
+    (:70-73), balanced model (:78-85), and the state (m, P) initialised on the first global iteration
+    only (:127-131) -- the smoothed mean and covariance of step 1 start the next filter pass."""
+    return _giekf(w, x, y, ss, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, None, nargout, debug_cov)
+
+
 def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
                                        g_iter, l_iter, constraints, w_fixed, tune_hypers, nargout=6, debug_cov=False):
     """Globally iterated EKF + RTS smoother, the comparison variant of the EP entry points.
@@ -316,9 +324,17 @@ def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, n
     runs it, experiments/train_model.m:226,239-240): ``(energy, zeros)`` when ``xt`` is empty,
     otherwise ``(Eft, Varft, Covft, lb, ub, out)``.  ``mom`` is ignored, as in the reference
     (its measurement model is hard-wired, :133-138)."""
+    return _giekf(w, x, y, ss, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter,
+                  (constraints, w_fixed, tune_hypers), nargout, debug_cov)
+
+
+def _giekf(w, x, y, ss, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, constrained, nargout, debug_cov):
     import scipy.linalg as sla
     yall, return_ind = merge_inputs(x, y, xt)
-    lik_param, param1, param2, Wnmf = _unpack_constrained(w, num_lik_params, D, N, constraints, w_fixed, tune_hypers)
+    if constrained is None:
+        lik_param, param1, param2, Wnmf = _unpack_log(w, num_lik_params, D, N)
+    else:
+        lik_param, param1, param2, Wnmf = _unpack_constrained(w, num_lik_params, D, N, *constrained)
     F, L, Qc, H, Pinf = ss(x, param1, param2, kernel1, kernel2)[:5]
     F, L, H, Pinf = ssmodel.balance(F, L, H, Pinf)                      # :113-120
     sigma2 = float(np.exp(np.asarray(lik_param, float).ravel()[0]))
@@ -347,8 +363,9 @@ def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, n
         bufs[nm] = np.zeros(shapes[nm])
         setattr(o, nm, _lib.dptr(bufs[nm]))
     yb = _lib.as_f64(yall)
-    status = _lib.lib().nsagp_giekf(C.byref(cm), Wf.ctypes.data_as(_lib.c_double_p), sigma2, int(g_iter), int(l_iter),
-                                    _lib.dptr(yb), T, _lib.MODE_PREDICT if predict else _lib.MODE_NLZ, C.byref(o))
+    call = _lib.lib().nsagp_giekf if constrained is not None else _lib.lib().nsagp_giekf_carry
+    status = call(C.byref(cm), Wf.ctypes.data_as(_lib.c_double_p), sigma2, int(g_iter), int(l_iter),
+                  _lib.dptr(yb), T, _lib.MODE_PREDICT if predict else _lib.MODE_NLZ, C.byref(o))
     if not predict:
         if status == -5:                                                # NSAGP_ERR_NAN: the reference returns NaN (:417-427)
             return float("nan"), np.zeros(np.size(w))

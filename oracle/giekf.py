@@ -47,15 +47,18 @@ def iekf_update1(M, P, y, D, N, H, Wnmf, R, iters):
     return M, P
 
 
-def giekf_core(A, Q, H, Pinf, sigma2, Wnmf, yall, D, N, g_iter, l_iter, return_ind, want_cov=False):
-    """Predict mode, gf_giekf_modulator_nmf_constraints.m:144-327."""
+def giekf_core(A, Q, H, Pinf, sigma2, Wnmf, yall, D, N, g_iter, l_iter, return_ind, want_cov=False, carry_cov=False):
+    """Predict mode, gf_giekf_modulator_nmf_constraints.m:144-327.  ``carry_cov``: the file without
+    constraints initialises (m, P) on the first global iteration only (gf_giekf_modulator_nmf.m:127-131)."""
     n = A.shape[0]; T = yall.size
     MS = np.zeros((n, T)); PS = np.zeros((n, n, T))
     out = {}
     maxDiffP_hist = []
     m = np.zeros(n)
+    P = Pinf.copy()
     for itt in range(1, g_iter + 1):
-        P = Pinf.copy()                      # m carries over, P is reset (:165-168)
+        if not carry_cov:
+            P = Pinf.copy()                  # m carries over, P is reset (:165-168)
         maxDiffP = 0.0
         PSP = PS.copy()
         for k in range(T):
@@ -119,5 +122,21 @@ def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, n
         A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)
         Eft, Varft, lb, ub, out = giekf_core(A, Q, H, Pinf, sigma2, Wnmf, yall, D, N, g_iter, l_iter,
                                              return_ind, want_cov)
+        return Eft, Varft, None, lb, ub, out
+    return giekf_energy(F, H, Pinf, sigma2, Wnmf, yall, D, N), np.zeros(np.size(w))
+
+
+def gf_giekf_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, want_cov=False):
+    """gf_giekf_modulator_nmf.m:1 (GradObj = 'off'): log-scale parameters (:70-73), balanced model (:78-85),
+    (m, P) carried across the global iterations (:127-131)."""
+    yall, return_ind = merge_inputs(x, y, xt)
+    lik_param, param1, param2, Wnmf = ssmodel.unpack_log(w, num_lik_params, D, N)
+    F, L, Qc, H, Pinf = ss(x, param1, param2, kernel1, kernel2)[:5]
+    F, L, H, Pinf, _ = ssmodel.balance_ss(F, L, H, Pinf)
+    sigma2 = math.exp(float(np.asarray(lik_param).ravel()[0]))
+    if xt is not None and np.size(xt) > 0:
+        A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)
+        Eft, Varft, lb, ub, out = giekf_core(A, Q, H, Pinf, sigma2, Wnmf, yall, D, N, g_iter, l_iter,
+                                             return_ind, want_cov, carry_cov=True)
         return Eft, Varft, None, lb, ub, out
     return giekf_energy(F, H, Pinf, sigma2, Wnmf, yall, D, N), np.zeros(np.size(w))

@@ -107,3 +107,33 @@ def test_giekf_energy_matches_oracle(nsagp, gpu_lib):
     eg2, _ = nsagp.gf_giekf_modulator_nmf_constraints(w, pb["t"], y2, pb["ss_gpu"], None, None, "matern32", "matern52",
                                                       1, D, N, 1, 1, cons, wf, tune)
     assert np.isnan(eg2)
+
+
+@pytest.mark.parametrize("form", [1, 2])
+def test_giekf_plain_entry_carries_covariance(nsagp, gpu_lib, giekf_form, form):
+    """gf_giekf_modulator_nmf (no constraints): log-scale w, (m, P) carried across global iterations."""
+    from oracle import giekf
+    D, N, T, k1, k2 = 5, 2, 140, "exp", "matern52"
+    pb = make_problem(nsagp, D, N, T, k1, k2, seed=77, kind="power", p=9, gaps=True, w_lik=1e-2)
+    w = pb["hyp"].pack_log()
+    Eo, Vo, _, lbo, ubo, oo = giekf.gf_giekf_modulator_nmf(w, pb["t"], pb["y"], pb["ss_ref"], None, pb["t"], k1, k2, 1, D, N, 3, 1,
+                                                           want_cov=True)
+    giekf_form(form, 9, 4)
+    Eg, Vg, _, lbg, ubg, og = nsagp.gf_giekf_modulator_nmf(w, pb["t"], pb["y"], pb["ss_gpu"], None, pb["t"], k1, k2, 1, D, N, 3, 1,
+                                                           debug_cov=True)
+    tol = TOL if form == 1 else 1e-6
+    assert rel_err(Eg, Eo) < tol and rel_err(Vg, Vo) < tol and rel_err(lbg, lbo) < tol and rel_err(ubg, ubo) < tol
+    assert rel_err(og["MS"], oo["MS"]) < tol and rel_err(og["PS"], oo["PS"]) < tol and rel_err(og["PF"], oo["PF"]) < tol
+    # the carried covariance matters: with P reset every iteration the filtered covariance of step 1 would be the prior's
+    oc = giekf.giekf_core(*_dense_model(pb, k1, k2, D, N), pb["y"], D, N, 3, 1, np.arange(T), want_cov=True)[4]
+    assert rel_err(oo["PF"][:, :, 0], oc["PF"][:, :, 0]) > 1e-3
+
+
+def _dense_model(pb, k1, k2, D, N):
+    import math
+    from oracle import ssmodel
+    lik_param, param1, param2, Wnmf = ssmodel.unpack_log(pb["hyp"].pack_log(), 1, D, N)
+    F, L, Qc, H, Pinf = pb["ss_ref"](pb["t"], param1, param2, k1, k2)[:5]
+    F, L, H, Pinf, _ = ssmodel.balance_ss(F, L, H, Pinf)
+    A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)
+    return A, Q, H, Pinf, math.exp(float(np.ravel(lik_param)[0])), Wnmf
