@@ -202,6 +202,19 @@ int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_
 /* Device time of the last nsagp_giekf call on this thread: ms[0] filter passes, ms[1] smoother passes (CUDA events). */
 int nsagp_giekf_timings(double* ms, int32_t n);
 
+/* Monte-Carlo reconstruction of the signal and of the NMF components from the posterior marginals -- the consumer of
+ * Eft / Varft in every demo (demo_toy_modulators_nmf.m:119-165; experiments/missing_data_music.m:138-176 with
+ * sqrt_model = 1: sig = sum_d sqrt(W link(g))_d z_d).  Eft, Varft: M-by-T column-major (M = D + N); W: D-by-N
+ * column-major; link = log(1 + exp(g - link_shift)); s samples per step.
+ * Z: standard-normal draws, T-by-s-by-M column-major (page i belongs to latent i; a wrapper that fills the pages
+ * with randn(T,s) in the order i = 1, D+1, 2, D+2, ... reproduces the reference's random stream), or NULL: the
+ * draws are generated on the device (Philox4x32-10 keyed by `seed`, Box-Muller), nothing but the marginals is read.
+ * Outputs: Esig, Vsig [T] (mean, var with the N-1 normalisation over the s samples); Eft_mod, Varft_mod N-by-T
+ * (may be NULL). */
+int nsagp_mc_reconstruct(int32_t D, int32_t N, int64_t T, int32_t s, const double* Eft, const double* Varft, const double* W,
+                         double link_shift, int32_t sqrt_model, const double* Z, uint64_t seed, double* Esig, double* Vsig,
+                         double* Eft_mod, double* Varft_mod);
+
 /* Batched forms: B independent problems of equal shapes (clips x hyper-parameter
  * grid x finite-difference perturbations; what fminunc does around the nlZ mode,
  * demo_toy_modulators_nmf.m:100-104).  models/liks/tables/outs are arrays of B

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libnsagp.so")
 _SOURCES = ["api.cu", "api_full.inc", "common.cuh", "mom.cuh", "momcta.cuh", "mombatch.cuh", "lookup.cuh", "ihgp.cuh",
-            "gfep.cuh", "adfcta.cuh", "fastmath.cuh", "scan.cuh", "ekf.cuh", "ekfscan.cuh", "api_ekf.inc", "api_chunk.inc", "api_tables.inc"]
+            "gfep.cuh", "adfcta.cuh", "fastmath.cuh", "scan.cuh", "ekf.cuh", "ekfscan.cuh", "mcrec.cuh", "api_mc.inc", "api_ekf.inc", "api_chunk.inc", "api_tables.inc"]
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -111,6 +111,8 @@ def lib():
     L.nsagp_plan_set_adf_form.argtypes = [C.c_void_p, C.c_int]
     L.nsagp_giekf.argtypes = [C.POINTER(Model), c_double_p, C.c_double, C.c_int32, C.c_int32, c_double_p, C.c_int64,
                               C.c_int32, C.POINTER(Outputs)]
+    L.nsagp_mc_reconstruct.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_double,
+                                       C.c_int32, c_double_p, C.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p]
     L.nsagp_giekf_carry.argtypes = L.nsagp_giekf.argtypes
     L.nsagp_giekf_config.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.nsagp_giekf_timings.argtypes = [c_double_p, C.c_int32]
@@ -128,7 +130,7 @@ EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_s
            "nsagp_ep_ihgp_batch", "nsagp_ep_full_batch", "nsagp_plan_create", "nsagp_plan_run",
            "nsagp_plan_fetch", "nsagp_plan_destroy", "nsagp_plan_timings", "nsagp_plan_keep_pf",
            "nsagp_plan_set_adf_form", "nsagp_fastmath_eval", "nsagp_release_cache", "nsagp_giekf", "nsagp_plan_set_range",
-           "nsagp_plan_stage", "nsagp_ihgp_tables", "nsagp_giekf_config", "nsagp_giekf_timings", "nsagp_giekf_carry"]
+           "nsagp_plan_stage", "nsagp_ihgp_tables", "nsagp_giekf_config", "nsagp_giekf_timings", "nsagp_giekf_carry", "nsagp_mc_reconstruct"]
 
 
 def check(status):

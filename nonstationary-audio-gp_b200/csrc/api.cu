@@ -18,6 +18,7 @@
 #include "adfcta.cuh"
 #include "ekf.cuh"
 #include "ekfscan.cuh"
+#include "mcrec.cuh"
 
 using namespace nsagp;
 
@@ -941,6 +942,7 @@ int plan_reset(nsagp_plan* pl) {
 #include "api_ekf.inc"
 #include "api_chunk.inc"
 #include "api_tables.inc"
+#include "api_mc.inc"
 
 extern "C" {
 
@@ -1060,6 +1062,12 @@ int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_
 int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                       const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
   return giekf_impl(model, W, sigma2, g_iter, l_iter, 1, y, T, mode, out);
+}
+
+int nsagp_mc_reconstruct(int32_t D, int32_t N, int64_t T, int32_t s, const double* Eft, const double* Varft, const double* W,
+                         double link_shift, int32_t sqrt_model, const double* Z, uint64_t seed, double* Esig, double* Vsig,
+                         double* Eft_mod, double* Varft_mod) {
+  return mc_reconstruct_impl(D, N, T, s, Eft, Varft, W, link_shift, sqrt_model, Z, seed, Esig, Vsig, Eft_mod, Varft_mod);
 }
 
 int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_per_segment) {

@@ -45,13 +45,20 @@ class IhgpTables:
         return pp, pg
 
 
-def build_tables(model, want_smoother=True, native=True):
+# Which Riccati solver build_tables uses by default (see its docstring).  The parity tests switch this off so
+# that kernels and oracle run on bitwise identical tables; the solvers are compared separately.
+DEFAULT_NATIVE = True
+
+
+def build_tables(model, want_smoother=True, native=None):
     """Solve the per-block DAREs and interpolate (``model``: ssmodel.BlockModel,
     with Q already symmetrised as in ihgp_ep_modulator_nmf.m:97).
 
     native=True: the library's own host routine (C ABI ``nsagp_ihgp_tables``: doubling algorithm
     in long double, a few milliseconds).  native=False: the same tables through SciPy's generic
     Riccati / Lyapunov solvers (what the oracle uses; ~0.3 s) -- kept as the cross-check."""
+    if native is None:
+        native = DEFAULT_NATIVE
     if native:
         return _build_tables_native(model, want_smoother)
     r = np.logspace(-2, 4, N_FINE)

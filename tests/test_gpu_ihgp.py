@@ -77,3 +77,23 @@ def test_ihgp_nlz_matches_oracle(nsagp, gpu_lib, constrained):
         eg, gg = nsagp.ihgp_ep_modulator_nmf_constraints(*a, cons, wf, tune)
     assert abs(eg - eo) < TOL_SEQ * abs(eo)
     assert np.all(gg == 0) and gg.shape == go.shape      # the reference's gradient is identically zero
+
+
+def test_native_tables_end_to_end(nsagp, gpu_lib):
+    """The library's own table routine (nsagp_ihgp_tables, doubling algorithm) instead of SciPy's generic Riccati
+    solver: the tables differ by the solvers' accuracy (<= 1e-10 in the max norm, test_host_logic.py), the
+    posterior by what that perturbation propagates to -- bounded here, not bit-level."""
+    from conftest import make_problem, rel_err
+    D, N, T = 4, 2, 300
+    pb = make_problem(nsagp, D, N, T, "matern32", "matern52", seed=5, kind="power", p=9)
+    out = {}
+    for native in (False, True):
+        nsagp.tables.DEFAULT_NATIVE = native
+        try:
+            out[native] = nsagp.ihgp_ep_modulator_nmf(pb["w"], pb["t"], pb["y"], pb["ss_gpu"], pb["mom_gpu"], pb["t"], "matern32",
+                                                      "matern52", 1, D, N, 0.5, [0.5, 0.5, 0.5], 3)
+        finally:
+            nsagp.tables.DEFAULT_NATIVE = False
+    e = rel_err(out[True][0], out[False][0]); v = rel_err(out[True][1], out[False][1])
+    print("native vs SciPy tables: Eft %.2e Varft %.2e" % (e, v))
+    assert e < 1e-5 and v < 1e-5

@@ -144,3 +144,24 @@ def test_lookup_rules():
     assert ihgp_ep._lookup_filter(r, 1e9) == 199
     assert ihgp_ep._lookup_filter(r, r[17]) == 17
     assert ihgp_ep._lookup_filter(r, 1e30) == 0          # all |r - R| round to R: tie -> first
+
+
+def test_mc_reconstruction_oracle_known_answers():
+    """oracle/mcrec.py: with zero marginal variances the reconstruction is the deterministic
+    sum_d (W link(g))_d z_d (demo_toy_modulators_nmf.m:125-127 ``sig_mean``); with only subband
+    uncertainty the sample mean / variance converge to the exact Gaussian moments."""
+    from oracle import mcrec
+    rng = np.random.default_rng(0)
+    D, N, T, s = 5, 2, 40, 20000
+    Eft = rng.standard_normal((D + N, T)); W = rng.random((D, N))
+    Z = rng.standard_normal((T, 8, D + N))
+    E, V, Em, Vm = mcrec.reconstruct(Eft, np.zeros_like(Eft), W, Z)
+    sig_mean = np.sum((W @ np.log(1 + np.exp(Eft[D:]))) * Eft[:D], axis=0)
+    assert np.allclose(E, sig_mean, rtol=1e-13) and np.allclose(V, 0, atol=1e-25)
+    assert np.allclose(Em, np.log(1 + np.exp(Eft[D:])), rtol=1e-13)
+    Varft = np.zeros_like(Eft); Varft[:D] = rng.uniform(0.1, 0.5, (D, T))
+    Z = rng.standard_normal((T, s, D + N))
+    E, V, _, _ = mcrec.reconstruct(Eft, Varft, W, Z, link_shift=1.0, sqrt_model=True)
+    amp = np.sqrt(W @ np.log(1 + np.exp(Eft[D:] - 1.0)))
+    assert np.allclose(V, np.sum(amp ** 2 * Varft[:D], axis=0), rtol=0.08)
+    assert np.max(np.abs(E - np.sum(amp * Eft[:D], axis=0)) / np.sqrt(V / s)) < 5
