@@ -194,7 +194,7 @@ int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, 
 /* Form of the dense RTS pass of nsagp_giekf (gf_giekf_modulator_nmf_constraints.m:221-253):
  * smoother_form 0 = automatic (the parallel scan over time on the FP64 tensor cores when n <= 80, csrc/ekfscan.cuh),
  * 1 = the first-generation kernels (filter and a smoother that is sequential in time; kept as a cross-check),
- * 2 = scan (error if n > 80).  chunk_len (0 = 64): steps composed per CTA;
+ * 2 = scan (error if n > 80).  chunk_len (0 = automatic, 16..256 depending on T): steps composed per CTA;
  * chunks_per_segment (0 = 2 x SM count): the scan works through the signal in segments of that many chunks,
  * which bounds its scratch memory (n^2 doubles per step of a segment).  Process-wide setting. */
 int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_per_segment);

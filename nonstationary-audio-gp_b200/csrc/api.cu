@@ -1074,7 +1074,7 @@ int nsagp_giekf_config(int32_t smoother_form, int32_t chunk_len, int32_t chunks_
   if (smoother_form < 0 || smoother_form > 2 || chunk_len < 0 || chunks_per_segment < 0)
     return fail(NSAGP_ERR_INVALID, "smoother_form must be 0, 1 or 2; chunk_len, chunks_per_segment >= 0");
   g_giekf_cfg.form = smoother_form;
-  g_giekf_cfg.chunk_len = chunk_len > 0 ? chunk_len : 64;
+  g_giekf_cfg.chunk_len = chunk_len;
   g_giekf_cfg.seg_chunks = chunks_per_segment;
   return NSAGP_OK;
 }

@@ -26,7 +26,8 @@
 
 namespace nsagp {
 
-constexpr int kDsThreads = 320;     // 10 warps = the 10 (5 tile rows x 2 tile columns) units of an 80 x 80 product
+constexpr int kDsThreads = 640;     // 20 warps = the 20 (5 tile rows x 1 tile column) units of an 80 x 80 product: 5 per scheduler
+constexpr int kDsCT = 1;            // tile columns per warp unit
 constexpr int kDsDinvLd = 12;       // leading dimension of the 8 x 8 inverse diagonal blocks (conflict-free fragments)
 
 template <int NP>
@@ -60,39 +61,50 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // C = op(X) * op(Y) over k tiles [kt0, kt1) (units of 4), all in shared memory; epi(r, c, v0, v1) receives
-// C(r, c) and C(r, c+1).  TX: op(X) = X'.  TY: op(Y) = Y'.  Warp w < NT owns tile rows (w&1)*RT.., tile columns 2*(w>>1)..+1.
+// C(r, c) and C(r, c+1).  TX: op(X) = X'.  TY: op(Y) = Y'.  Warp w < 2*NT/kDsCT owns tile rows (w&1)*RT.., tile columns
+// kDsCT*(w>>1)..  (DMMA issues at one per 16 cycles per scheduler: the warps must spread evenly over the four schedulers).
 template <int NP, bool TX, bool TY, class Epi>
 __device__ __forceinline__ void ds_gemm(const double* __restrict__ X, const double* __restrict__ Y, int kt0, int kt1, Epi epi) {
   constexpr int LD = Ds<NP>::LD, NT = Ds<NP>::NT, RT = Ds<NP>::RT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gr = lane >> 2, q = lane & 3;
-  if (warp >= NT) return;
-  const int tr0 = (warp & 1) * RT, tc0 = (warp >> 1) * 2;
-  double acc[RT][2][2];
+  constexpr int CT = kDsCT;
+  if (warp >= 2 * NT / CT) return;
+  const int tr0 = (warp & 1) * RT, tc0 = (warp >> 1) * CT;
+  double acc[RT][CT][2];
 #pragma unroll
-  for (int i = 0; i < RT; ++i) { acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0; }
-#pragma unroll 2
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
   for (int kt = kt0; kt < kt1; ++kt) {
     const int k = kt * 4 + q;
-    double a[RT], b[2];
+    double a[RT], b[CT];
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
       const int r = (tr0 + i) * 8 + gr;
       a[i] = TX ? X[k + r * LD] : X[r + k * LD];
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < CT; ++j) {
       const int c = (tc0 + j) * 8 + gr;
       b[j] = TY ? Y[c + k * LD] : Y[k + c * LD];
     }
 #pragma unroll
     for (int i = 0; i < RT; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      for (int j = 0; j < CT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
 #pragma unroll
   for (int i = 0; i < RT; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) epi((tr0 + i) * 8 + gr, (tc0 + j) * 8 + 2 * q, acc[i][j][0], acc[i][j][1]);
+    for (int j = 0; j < CT; ++j) epi((tr0 + i) * 8 + gr, (tc0 + j) * 8 + 2 * q, acc[i][j][0], acc[i][j][1]);
+}
+
+// Pull the n*n doubles at g towards L2 (one 128-byte line per thread) ahead of the step that reads them.
+__device__ __forceinline__ void ds_prefetch_l2(const double* g, int n) {
+  const size_t bytes = (size_t)n * n * 8;
+  for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)g + o));
 }
 
 template <int NP>
@@ -207,6 +219,7 @@ ds_elements_kernel(const __grid_constant__ DsArgs g) {
   for (long long k = g.seg_k0 + blockIdx.x; k < g.seg_k1; k += gridDim.x) {
     __syncthreads();
     ds_load<NP>(Pm, a.PS + (size_t)k * a.ps_stride, n);
+    if (k + gridDim.x < g.seg_k1) ds_prefetch_l2(a.PS + (size_t)(k + gridDim.x) * a.ps_stride, n);
     for (int i = tid; i < NP; i += nth) mf[i] = (i < n) ? a.MS[k * n + i] : 0.0;
     // padding of X (zero) and of PSkp (identity)
     for (int i = tid; i < NP * NP; i += nth) {
@@ -394,6 +407,10 @@ ds_compose_kernel(const __grid_constant__ DsArgs g) {
       __syncthreads();
       ds_load<NP>(Gm, g.Gt + (size_t)s * nn, n);
       for (int i = tid; i < NP; i += nth) gk[i] = (i < n) ? g.gv[s * n + i] : 0.0;
+      if (s > s0) {
+        ds_prefetch_l2(g.Gt + (size_t)(s - 1) * nn, n);
+        ds_prefetch_l2(g.ekf.PS + (size_t)(g.seg_k0 + s - 1) * g.ekf.ps_stride, n);
+      }
       __syncthreads();
       // T1 = G La
       ds_gemm<NP, true, false>(Gm, La, 0, NP / 4, [&](int r, int c, double v0, double v1) {
@@ -528,6 +545,10 @@ ds_apply_kernel(const __grid_constant__ DsArgs g) {
       __syncthreads();
       ds_load<NP>(Gm, g.Gt + (size_t)s * nn, n);
       for (int i = tid; i < NP; i += nth) gk[i] = (i < n) ? g.gv[s * n + i] : 0.0;
+      if (s > s0) {
+        ds_prefetch_l2(g.Gt + (size_t)(s - 1) * nn, n);
+        ds_prefetch_l2(g.ekf.PS + (size_t)(k - 1) * g.ekf.ps_stride, n);
+      }
       __syncthreads();
       ds_gemm<NP, true, false>(Gm, Ps, 0, NP / 4, [&](int r, int c, double v0, double v1) {
         T1[r + c * LD] = v0; T1[r + (c + 1) * LD] = v1;

@@ -57,7 +57,7 @@ def run(T, form, chunk_len=0, seg_chunks=0, g_iter=1, keep=None):
             best = ms.copy()
     L.check(L.lib().nsagp_giekf_config(0, 0, 0))
     rec = dict(config="C4 gf_giekf D=32 N=3 n=%d T=%d g_iter=%d gaps" % (n, T, g_iter),
-               smoother="scan (DMMA)" if form != 1 else "sequential", chunk_len=chunk_len or 64, seg_chunks=seg_chunks,
+               smoother="scan (DMMA)" if form != 1 else "first-generation kernels", chunk_len=chunk_len or "auto", seg_chunks=seg_chunks,
                filter_ms=float(best[0]), smoother_ms=float(best[1]),
                filter_us_per_step=float(best[0]) * 1e3 / (T * g_iter), smoother_us_per_step=float(best[1]) * 1e3 / (T * g_iter),
                steps_per_s=T * g_iter / best.sum() * 1e3,
@@ -71,7 +71,7 @@ def run(T, form, chunk_len=0, seg_chunks=0, g_iter=1, keep=None):
 def main():
     T_scan = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
     T_seq = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
-    chunk_lens = [int(v) for v in sys.argv[3:]] or [64]
+    chunk_lens = [int(v) for v in sys.argv[3:]] or [0]
     a, b = {}, {}
     run(T_seq, 1, keep=a)
     run(T_seq, 2, keep=b)
