@@ -10,7 +10,9 @@
 // entry-point names and argument lists):
 //   out = nsagp_mex('ep_ihgp', model, lik, ep, tables, yall, mode)
 //   out = nsagp_mex('ep_full', model, lik, ep, [],     yall, mode)
-//   out = nsagp_mex('giekf', model, W, sigma2, g_iter, l_iter, yall, mode)
+//   out = nsagp_mex('giekf', model, W, sigma2, g_iter, l_iter, yall, mode)        (P reset every global iteration)
+//   out = nsagp_mex('giekf_carry', model, W, sigma2, g_iter, l_iter, yall, mode)  (gf_giekf_modulator_nmf.m: m, P carried)
+//   [Esig, Vsig, Eft_mod, Varft_mod] = nsagp_mex('mc_reconstruct', Eft, Varft, W, link_shift, sqrt_model, s, Z_or_seed)
 //   [lZ, dlZ, d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)
 // model  : struct with fields D, N, bz, bg, A, Q, Pinf, h   (packed per-latent blocks, see nsagp_model)
 // lik    : struct with fields kind, sn2, link_shift, W (D-by-N), wn (1-by-S), xn (N-by-S)
@@ -120,7 +122,7 @@ void ep_call(bool ihgp, int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs
   plhs[0] = s;
 }
 
-void giekf_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+void giekf_call(bool carry, int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: out = nsagp_mex('giekf', model, W, sigma2, g_iter, l_iter, yall, mode)");
   (void)nlhs;
   nsagp_model model;
@@ -138,13 +140,37 @@ void giekf_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (mode == NSAGP_MODE_PREDICT) {
     put(s, "Eft", M, T, &o.Eft); put(s, "Varft", M, T, &o.Varft); put(s, "lb", M, T, &o.lb); put(s, "ub", M, T, &o.ub);
     put(s, "MF", n, T, &o.MF); put(s, "MS", n, T, &o.MS); put(s, "maxDiffP", 1, g_iter, &o.maxDiffP);
-    check(nsagp_giekf(&model, W, sigma2, g_iter, l_iter, y, T, mode, &o));
+    check((carry ? nsagp_giekf_carry : nsagp_giekf)(&model, W, sigma2, g_iter, l_iter, y, T, mode, &o));
   } else {
     put(s, "edata", 1, 1, &o.edata);
-    const int st = nsagp_giekf(&model, W, sigma2, g_iter, l_iter, y, T, mode, &o);
+    const int st = (carry ? nsagp_giekf_carry : nsagp_giekf)(&model, W, sigma2, g_iter, l_iter, y, T, mode, &o);
     if (st != NSAGP_ERR_NAN) check(st);          // a NaN energy is a value the reference returns to the optimiser
   }
   plhs[0] = s;
+}
+
+// [Esig, Vsig, Eft_mod, Varft_mod] = nsagp_mex('mc_reconstruct', Eft, Varft, W, link_shift, sqrt_model, s, Z_or_seed)
+// Z_or_seed: a T-by-s-by-M array of standard-normal draws (page i = latent i), or a scalar seed.
+void mc_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: [Esig,Vsig,Eft_mod,Varft_mod] = nsagp_mex('mc_reconstruct', Eft, Varft, W, link_shift, sqrt_model, s, Z_or_seed)");
+  const int32_t D = (int32_t)mxGetM(prhs[3]), N = (int32_t)mxGetN(prhs[3]);
+  const int64_t T = (int64_t)mxGetN(prhs[1]);
+  const int32_t s = (int32_t)mxGetScalar(prhs[6]);
+  if ((int64_t)mxGetM(prhs[1]) != D + N) mexErrMsgIdAndTxt("nsagp:arg", "Eft must be (D+N)-by-T");
+  const bool seeded = mxGetNumberOfElements(prhs[7]) == 1;
+  if (!seeded && (int64_t)mxGetNumberOfElements(prhs[7]) != T * s * (D + N)) mexErrMsgIdAndTxt("nsagp:arg", "Z must be T-by-s-by-(D+N)");
+  mxArray* Es = mxCreateDoubleMatrix(T, 1, mxREAL);
+  mxArray* Vs = mxCreateDoubleMatrix(T, 1, mxREAL);
+  mxArray* Em = mxCreateDoubleMatrix(N, T, mxREAL);
+  mxArray* Vm = mxCreateDoubleMatrix(N, T, mxREAL);
+  check(nsagp_mc_reconstruct(D, N, T, s, dbl(prhs[1], "Eft"), dbl(prhs[2], "Varft"), dbl(prhs[3], "W"), mxGetScalar(prhs[4]),
+                             (int32_t)mxGetScalar(prhs[5]), seeded ? nullptr : dbl(prhs[7], "Z"),
+                             seeded ? (uint64_t)mxGetScalar(prhs[7]) : 0, mxGetDoubles(Es), mxGetDoubles(Vs), mxGetDoubles(Em),
+                             mxGetDoubles(Vm)));
+  plhs[0] = Es;
+  if (nlhs > 1) plhs[1] = Vs; else mxDestroyArray(Vs);
+  if (nlhs > 2) plhs[2] = Em; else mxDestroyArray(Em);
+  if (nlhs > 3) plhs[3] = Vm; else mxDestroyArray(Vm);
 }
 
 void mom_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
@@ -172,7 +198,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   const std::string c(cmd);
   if (c == "ep_ihgp") ep_call(true, nlhs, plhs, nrhs, prhs);
   else if (c == "ep_full") ep_call(false, nlhs, plhs, nrhs, prhs);
-  else if (c == "giekf") giekf_call(nlhs, plhs, nrhs, prhs);
+  else if (c == "giekf") giekf_call(false, nlhs, plhs, nrhs, prhs);
+  else if (c == "giekf_carry") giekf_call(true, nlhs, plhs, nrhs, prhs);
+  else if (c == "mc_reconstruct") mc_call(nlhs, plhs, nrhs, prhs);
   else if (c == "mom") mom_call(nlhs, plhs, nrhs, prhs);
   else if (c == "version") plhs[0] = mxCreateString(nsagp_version());
   else mexErrMsgIdAndTxt("nsagp:arg", "unknown command '%s'", cmd);

@@ -18,6 +18,8 @@ mxArray* mxGetField(const mxArray*, mwSize, const char*);
 double* mxGetDoubles(const mxArray*);
 double mxGetScalar(const mxArray*);
 size_t mxGetNumberOfElements(const mxArray*);
+size_t mxGetM(const mxArray*);
+size_t mxGetN(const mxArray*);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
 mxArray* mxCreateString(const char*);

@@ -51,6 +51,11 @@ FULL_METRICS = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM % of peak"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe % (active SMs)"),
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 inst % (active SMs)"),
+    ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "FP64 tensor (DMMA) pipe % (active SMs)"),
+    ("sm__ops_path_tensor_src_fp64.sum.per_second", "FP64 tensor ops/ns, chip (peak 37170)"),
+    ("sm__ops_path_tensor_src_fp64.sum.pct_of_peak_sustained_elapsed", "FP64 tensor ops % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory wavefronts % of peak"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__cycles_elapsed.max", "cycles"),
