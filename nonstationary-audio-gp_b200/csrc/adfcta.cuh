@@ -35,20 +35,13 @@ constexpr int kAdfMaxMomThreads = 352;     // 11 moment warps + the Kalman warp 
 // R moves by a few grid cells per step, so ten thresholds around the previous row are loaded at
 // once and counted; the binary search only runs when the answer lies outside that window.
 __device__ __forceinline__ int lookup_by_ttau(const double* cthr, int nr, double tt, int hint) {
-  const int last = nr - 2;
-  const int h = min(max(hint, 0), nr - 1);
-  const int lo = max(h - 5, 0), hi = min(h + 4, last);
+  // cthr is surrounded by kCthrPad sentinels (+Inf below index 0, -Inf above nr-2): no bounds checks in the window
+  const int w0 = min(max(hint, 0), nr - 1) - 5;
+  const double* w = cthr + w0;
   int cnt = 0;
-  bool first = false, end = false;
 #pragma unroll
-  for (int j = 0; j < 10; ++j) {
-    const int i = min(lo + j, hi);
-    const bool le = tt <= cthr[i];
-    cnt += (lo + j <= hi && le) ? 1 : 0;
-    if (j == 0) first = le;
-    end = le;                               // after the loop: the comparison at hi
-  }
-  if ((lo == 0 || first) && (hi == last || !end)) return lo + cnt;
+  for (int j = 0; j < 10; ++j) cnt += (tt <= w[j]) ? 1 : 0;
+  if (cnt > 0 && cnt < 10) return w0 + cnt;  // the change from "<=" to ">" lies inside the window
   int a = 0, b = nr - 1;
   while (a < b) {
     const int mid = (a + b) >> 1;
@@ -66,7 +59,7 @@ struct AdfSmem {
     wn = o; o += S;
     xn = o; o += kNP * S;
     q = o; o += fullstate ? M * BM * BM : 0;
-    cthr = o; o += tables ? nr - 1 : 0;
+    cthr = o; o += tables ? nr - 1 + 2 * kCthrPad : 0;
     hph = o; o += tables ? M * (nr + 1) : 0;
     wtab = o; o += tables ? M * (nr + 1) * BM : 0;
     sdt = o; o += tables ? N * (nr + 1) : 0;
@@ -120,13 +113,13 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   for (int i = tid; i < P.S; i += nthreads) s_wn[i] = P.wn[i];
   for (int i = tid; i < kNP * P.S; i += nthreads) s_xn[i] = P.xn[i];
   // steady-state tables: shared memory when they fit (TABS), else straight from HBM/L2
-  const double* cthr = TABS ? sm + L.cthr : P.cthr;
+  const double* cthr = TABS ? sm + L.cthr + kCthrPad : P.cthr;
   const double* hphtab = TABS ? sm + L.hph : P.HPHtab;
   const double* wtab = TABS ? sm + L.wtab : P.Wtab;
   const double* sdtab = TABS ? sm + L.sdt : P.SDtab;
   const double* rs2tab = TABS ? sm + L.rs2t : P.RS2tab;
   if (TABS) {
-    for (int i = tid; i < nr - 1; i += nthreads) sm[L.cthr + i] = P.cthr[i];
+    for (int i = tid; i < nr - 1 + 2 * kCthrPad; i += nthreads) sm[L.cthr + i] = P.cthr[i - kCthrPad];
     for (int i = tid; i < M * (nr + 1); i += nthreads) sm[L.hph + i] = P.HPHtab[i];
     for (int i = tid; i < M * (nr + 1) * BM; i += nthreads) sm[L.wtab + i] = P.Wtab[i];
     for (int i = tid; i < P.N * (nr + 1); i += nthreads) { sm[L.sdt + i] = P.SDtab[i]; sm[L.rs2t + i] = P.RS2tab[i]; }

@@ -525,12 +525,17 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
           SDt[(size_t)j * (nr + 1) + row] = std::sqrt(v);
           RS2t[(size_t)j * (nr + 1) + row] = 1.0 / v;
         }
+      // window look-up (adfcta.cuh: lookup_by_ttau) reads 10 thresholds around the previous row without bounds checks:
+      // kCthrPad sentinels on either side (+Inf: "ttau <= c" holds; -Inf: it does not)
+      std::vector<double> cthr_pad(cthr.size() + 2 * kCthrPad);
+      for (int i = 0; i < kCthrPad; ++i) { cthr_pad[i] = INFINITY; cthr_pad[kCthrPad + cthr.size() + i] = -INFINITY; }
+      std::copy(cthr.begin(), cthr.end(), cthr_pad.begin() + kCthrPad);
       double *dr, *dthr, *dcthr, *dWt, *dHPH, *dSD, *dRS2, *dG = nullptr, *dvm = nullptr;
       if ((rc = pl->arena.upload(&dr, r)) || (rc = pl->arena.upload(&dthr, thr)) || (rc = pl->arena.upload(&dWt, Wtab)) ||
-          (rc = pl->arena.upload(&dHPH, HPH)) || (rc = pl->arena.upload(&dcthr, cthr)) ||
+          (rc = pl->arena.upload(&dHPH, HPH)) || (rc = pl->arena.upload(&dcthr, cthr_pad)) ||
           (rc = pl->arena.upload(&dSD, SDt)) || (rc = pl->arena.upload(&dRS2, RS2t)))
         return cleanup(rc);
-      P.cthr = dcthr; P.SDtab = dSD; P.RS2tab = dRS2;
+      P.cthr = dcthr + kCthrPad; P.SDtab = dSD; P.RS2tab = dRS2;
       if (tb.PG && ((rc = pl->arena.upload(&dG, Gtab)) || (rc = pl->arena.upload(&dvm, vmtab)))) return cleanup(rc);
       P.r = dr; P.thr = dthr; P.Wtab = dWt; P.HPHtab = dHPH; P.Gtab = dG; P.vmtab = dvm;
     } else {

@@ -11,6 +11,7 @@ constexpr int kMaxSites = 64;    // D + N
 constexpr int kWarp = 32;
 constexpr double kInvSqrt2Pi = 0.39894228040143267793994605993438;
 constexpr double kJitter = 1e-10;          // likModulatorNMFPower.m:28
+constexpr int kCthrPad = 8;                // sentinels on either side of the ttau thresholds (window look-up)
 constexpr double kLookupBig = 1e12;        // above this the nearest-neighbour search is done by brute force
 
 // Per-problem constant data resident in HBM (built once by the plan).
@@ -39,7 +40,8 @@ struct DevProblem {
   const double* HPHtab;          // [M][nr+1]      h*PP*h'
   const double* Gtab;            // [M][nr][BM*BM] smoother gain
   const double* vmtab;           // [M][nr]        h*Ps*h'
-  const double* cthr;            // [nr-1] the same thresholds expressed on ttau: 1/ttau >= thr[i]  <=>  ttau <= cthr[i]
+  const double* cthr;            // [nr-1] the same thresholds expressed on ttau: 1/ttau >= thr[i]  <=>  ttau <= cthr[i];
+                                 // kCthrPad sentinels (+Inf below index 0, -Inf above nr-2) surround the array
   const double* SDtab;           // [N][nr+1]      sqrt(h*PP*h') of the modulator blocks
   const double* RS2tab;          // [N][nr+1]      1/(h*PP*h')
 };
