@@ -32,16 +32,33 @@ constexpr int kAdfMaxMomThreads = 352;     // 11 moment warps + the Kalman warp 
 
 // idx = #{i : thr[i] <= 1/tt} = #{i : tt <= cthr[i]} (cthr descending, nr-1 entries; host-built so
 // that the decision is bit-identical to the reference's min(abs(r-R)) with R = 1./ttau).
-// R moves by a few grid cells per step, so ten thresholds around the previous row are loaded at
-// once and counted; the binary search only runs when the answer lies outside that window.
-__device__ __forceinline__ int lookup_by_ttau(const double* cthr, int nr, double tt, int hint) {
-  // cthr is surrounded by kCthrPad sentinels (+Inf below index 0, -Inf above nr-2): no bounds checks in the window
-  const int w0 = min(max(hint, 0), nr - 1) - 5;
+// In the ADF sweep the sites of consecutive steps are unrelated (old sites are zero), so R jumps by decades from
+// step to step and a window around the previous row misses most of the time.  The row is guessed from the bits of
+// ttau instead: the high word of a double is a piecewise-linear log2 (error <= 0.086), the grid is log-spaced, so
+// guess = ga + gb * hi32(ttau) is within one row of the answer; six thresholds around the guess are loaded at once
+// and counted (the array carries kCthrPad sentinels on either side: no bounds checks).  A grid that is not
+// log-spaced only costs the binary search.
+struct TtauGuess { double a, b; };
+
+__device__ __forceinline__ TtauGuess make_ttau_guess(const double* r, int nr) {
+  // row position of R on the grid: (log10 R - log10 r0) * scale; R = 1/ttau; log2(ttau) ~ hi32/2^20 - 1023 + 0.043;
+  // #{thresholds <= R} ~ floor(position + 0.49) for arithmetic mid-point thresholds on a log-spaced grid
+  const double scale = (double)(nr - 1) / (log10(r[nr - 1]) - log10(r[0]));
+  const double l2 = 0.30102999566398120 * scale;
+  TtauGuess g;
+  g.b = -l2 / 1048576.0;
+  g.a = -log10(r[0]) * scale + (1023.0 - 0.043) * l2 + 0.49;
+  return g;
+}
+
+__device__ __forceinline__ int lookup_by_ttau(const double* cthr, int nr, double tt, const TtauGuess& g) {
+  const int guess = __double2int_rd(fma((double)__double2hiint(tt), g.b, g.a));
+  const int w0 = min(max(guess - 3, -kCthrPad), nr + 1);
   const double* w = cthr + w0;
   int cnt = 0;
 #pragma unroll
-  for (int j = 0; j < 10; ++j) cnt += (tt <= w[j]) ? 1 : 0;
-  if (cnt > 0 && cnt < 10) return w0 + cnt;  // the change from "<=" to ">" lies inside the window
+  for (int j = 0; j < 6; ++j) cnt += (tt <= w[j]) ? 1 : 0;
+  if (cnt > 0 && cnt < 6) return w0 + cnt;   // the change from "<=" to ">" lies inside the window
   int a = 0, b = nr - 1;
   while (a < b) {
     const int mid = (a + b) >> 1;
@@ -147,6 +164,7 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   const int off = P.off[n];
   const int b = P.off[n + 1] - off;
 
+  const TtauGuess guess = make_ttau_guess(P.r, nr);
   int idx;
   if (k0 == 0) {
     idx = nr;                                 // PP = Pinf at the first step (:246)
@@ -253,7 +271,7 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
 #pragma unroll
       for (int i = 0; i < BM; ++i) m[i] = fma(Wv[i], c, Am[i]);
       if (do_mom) {
-        idx = (tt > 2e-12) ? lookup_by_ttau(cthr, nr, tt, idx) : lookup_filter(P.r, P.thr, nr, 1.0 / tt);
+        idx = (tt > 2e-12) ? lookup_by_ttau(cthr, nr, tt, guess) : lookup_filter(P.r, P.thr, nr, 1.0 / tt);
       } else {
         idx = lookup_filter(P.r, P.thr, nr, R_ld);
       }
