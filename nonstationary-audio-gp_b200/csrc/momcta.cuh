@@ -123,11 +123,21 @@ __device__ __forceinline__ void mom_cta_points(const MomParams& p, const MomCtaT
       double ad = 0.0;
 #pragma unroll
       for (int j = 0; j < kNP; ++j) ad = fma(l[j], th.W[i][j], ad);
-      if (p.kind == 1) { a2[i] = ad; ad = sqrt_fast2_pos(ad); } // a = sqrt(W link): a.^2 is the argument itself
-      else a2[i] = ad * ad;
       a[i] = ad;
+    }
+    // one branch on the likelihood kind around all DPT evaluations (a branch per subband kept the DPT square
+    // roots in separate basic blocks, i.e. one after the other on the critical path)
+    if (p.kind == 1) {
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) { a2[i] = a[i]; a[i] = sqrt_fast2_pos(a[i]); }   // a = sqrt(W link): a.^2 is the argument itself
+    } else {
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) a2[i] = a[i] * a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DPT; ++i) {
       vs = fma(a2[i], s2z[i], vs);
-      ms = fma(ad, muz[i], ms);
+      ms = fma(a[i], muz[i], ms);
     }
     vs += __shfl_xor_sync(0xffffffffu, vs, 1);
     ms += __shfl_xor_sync(0xffffffffu, ms, 1);
