@@ -52,8 +52,9 @@ __device__ __forceinline__ TtauGuess make_ttau_guess(const double* r, int nr) {
 }
 
 __device__ __forceinline__ int lookup_by_ttau(const double* cthr, int nr, double tt, const TtauGuess& g) {
-  const int guess = __double2int_rd(fma((double)__double2hiint(tt), g.b, g.a));
-  const int w0 = min(max(guess - 3, -kCthrPad), nr + 1);
+  // clamped to the table: R below / above the grid then finds its answer (row 0 / nr-1) in the middle of the window
+  const int guess = min(max(__double2int_rd(fma((double)__double2hiint(tt), g.b, g.a)), 0), nr - 1);
+  const int w0 = guess - 3;
   const double* w = cthr + w0;
   int cnt = 0;
 #pragma unroll
