@@ -82,16 +82,23 @@ __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, c
   double vs = 0.0, ms = 0.0;
 #pragma unroll
   for (int d = 0; d < DP; ++d) {
+    double ad = 0.0;
     if (d < p.D) {
-      double ad = 0.0;
 #pragma unroll
       for (int j = 0; j < kNP; ++j) ad = fma(l[j], p.W[d * kNP + j], ad);
-      if (p.kind == 1) ad = FAST ? sqrt_fast2(ad) : sqrt(ad);
-      a[d] = ad;
-      vs = fma(ad * ad, s2z[d * stride], vs);
-      ms = fma(ad, muz[d * stride], ms);
-    } else {
-      a[d] = 0.0;
+    }
+    a[d] = ad;
+  }
+  if (p.kind == 1) {               // one branch around all square roots: they interleave instead of queueing up
+#pragma unroll
+    for (int d = 0; d < DP; ++d)
+      if (d < p.D) a[d] = FAST ? sqrt_fast2(a[d]) : sqrt(a[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < DP; ++d) {
+    if (d < p.D) {
+      vs = fma(a[d] * a[d], s2z[d * stride], vs);
+      ms = fma(a[d], muz[d * stride], ms);
     }
   }
   const double v = noise + vs;
@@ -197,7 +204,7 @@ __device__ __forceinline__ void warp_reduce_array(double (&v)[K], int lane) {
 // All 32 lanes must call.  mu/s2: D+N values, contiguous (shared memory).
 // On return lane n < D+N holds (d1, d2) of site n; every lane gets lZ.
 // Requires D <= DP, D+N <= 32, N <= kNP.
-template <int DP>
+template <int DP, bool FAST = false>
 __device__ __forceinline__ double mom_warp(const MomParams& p, double alpha, double y,
                                            const double* mu, const double* s2, int lane,
                                            double& d1, double& d2) {
@@ -207,7 +214,7 @@ __device__ __forceinline__ double mom_warp(const MomParams& p, double alpha, dou
   MomG g;
   mom_setup_g(g, p, mu + p.D, s2 + p.D, 1);
   const double noise = p.sn2 / alpha;
-  for (int s = lane; s < p.S; s += kWarp) mom_point<DP>(acc, p, g, s, y, noise, mu, s2, 1);
+  for (int s = lane; s < p.S; s += kWarp) mom_point<DP, FAST>(acc, p, g, s, y, noise, mu, s2, 1);
 
   // modulator sums: [g1 | g2] -> lane L holds entry L>>2
   double gv[2 * kNP];
