@@ -431,6 +431,7 @@ struct RtsScanElem {
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) s.P[i] = src[BM + i];
   }
+  __device__ __forceinline__ void prefetch(long long) {}
   __device__ __forceinline__ void get(long long k, Map& e) {
     RtsStep<BM> st;
     el.step(k, st);
@@ -664,6 +665,7 @@ struct KfScanElem {
     if (nlz) tt = fmax(tt, 0.0);
     return true;
   }
+  __device__ __forceinline__ void prefetch(long long) {}
   __device__ __forceinline__ void get(long long k, Map& e) {
     double tt, tn;
     sites(k, tt, tn);

@@ -229,6 +229,11 @@ __device__ __forceinline__ void affine_apply(const Affine<BM>& e, double (&m)[BM
 }
 
 // What the two IHGP mean recursions share (scan.cuh's Elem interface).
+// Hint the lines an element will read at step k towards L1: the element inputs (sites, means) do not depend on the
+// scan's running state, but every step of the walk stores (MS, E), so the compiler cannot hoist the next step's
+// loads itself and each step would wait for three dependent L2 round trips.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int BM>
 struct AffineElemBase {
   using Map = Affine<BM>;
@@ -305,6 +310,10 @@ struct FilterElem : AffineElemBase<BM> {
     }
   }
   __device__ __forceinline__ void get(long long k, Map& e) { get_impl(k, e, false); }
+  __device__ __forceinline__ void prefetch(long long k) {
+    const int M = P.M;
+    prefetch_l1(St.ttau + k * M + n); prefetch_l1(St.R + k * M + n); prefetch_l1(St.tnu + k * M + n);
+  }
   __device__ __forceinline__ void step(long long k, State& s) {
     Map e;
     get_impl(k, e, true);
@@ -368,6 +377,9 @@ struct SmootherElem : AffineElemBase<BM> {
     }
   }
   __device__ __forceinline__ void get(long long k, Map& e) { get_impl(k, e, false); }
+  __device__ __forceinline__ void prefetch(long long k) {
+    prefetch_l1(St.R + k * P.M + n); prefetch_l1(St.MS + k * P.n + off); prefetch_l1(St.E + k * P.M + n);
+  }
   __device__ __forceinline__ void step(long long k, State& s) {
     Map e;
     get_impl(k, e, true);

@@ -64,8 +64,10 @@ __global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const D
       Map e;
       const long long s0 = chunk * kScanSteps;
       const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
+      if (s0 + 1 < a.nsteps) el.prefetch(a.kfirst + a.dir * (s0 + 1));
       el.get(a.kfirst + a.dir * s0, acc);
       for (long long s = s0 + 1; s < s1; ++s) {
+        if (s + 2 < a.nsteps) el.prefetch(a.kfirst + a.dir * (s + 2));
         el.get(a.kfirst + a.dir * s, e);
         Elem::compose(acc, e);
       }
@@ -195,7 +197,11 @@ __global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const De
   Elem::load_state(s, s_state + ((size_t)c * M + n) * SW);
   const long long s0 = chunk * kScanSteps;
   const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
-  for (long long t = s0; t < s1; ++t) el.step(a.kfirst + a.dir * t, s);
+  if (s0 + 1 < a.nsteps) el.prefetch(a.kfirst + a.dir * (s0 + 1));
+  for (long long t = s0; t < s1; ++t) {
+    if (t + 2 < a.nsteps) el.prefetch(a.kfirst + a.dir * (t + 2));
+    el.step(a.kfirst + a.dir * t, s);
+  }
   el.finish_apply();
 }
 
