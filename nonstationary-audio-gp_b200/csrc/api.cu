@@ -789,7 +789,7 @@ int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, 
   CU(cudaFuncGetAttributes(&f1, scan_reduce_kernel<Elem>));
   CU(cudaFuncGetAttributes(&f3, scan_apply_kernel<Elem>));
   const int regs = std::max(f1.numRegs, f3.numRegs);
-  while (a.CH > 1 && 32 * a.CH * regs > 65536) a.CH >>= 1;
+  while (a.CH > 1 && pl->M * a.CH * regs > 65536) a.CH >>= 1;
   return NSAGP_OK;
 }
 
@@ -797,7 +797,7 @@ int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, 
 template <class Elem>
 int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  const dim3 block(32, a.CH);
+  const dim3 block(pl->M, a.CH);          // one thread per (latent, chunk): M <= 32 lanes in x, no warp-level operations in the scans
   const dim3 grid((unsigned)ntiles, pl->B);
   const size_t sm1 = (size_t)a.CH * pl->M * Elem::kMapDoubles * sizeof(double);
   if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
@@ -816,7 +816,7 @@ int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
 template <class Elem>
 int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev) {
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  const dim3 block(32, a.CH);
+  const dim3 block(pl->M, a.CH);          // one thread per (latent, chunk): M <= 32 lanes in x, no warp-level operations in the scans
   const dim3 grid((unsigned)ntiles, pl->B);
   const size_t sm3 = (size_t)a.CH * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
   if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));

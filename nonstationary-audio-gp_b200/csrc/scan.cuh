@@ -19,7 +19,7 @@
 //            entering every chunk (shared memory); every thread then re-applies the literal
 //            steps of its chunk and emits.  Only the chunk-entry states are re-associated.
 //
-// Thread layout: threadIdx.x = latent block n (coalesced M-contiguous site loads, 32 lanes),
+// Thread layout: threadIdx.x = latent block n (coalesced M-contiguous site loads; blockDim.x = M, so no idle lanes),
 // threadIdx.y = chunk within the CTA tile (CH chunks), grid = (tiles, signals).
 #pragma once
 #include "common.cuh"
