@@ -530,14 +530,24 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
       std::vector<double> cthr_pad(cthr.size() + 2 * kCthrPad);
       for (int i = 0; i < kCthrPad; ++i) { cthr_pad[i] = INFINITY; cthr_pad[kCthrPad + cthr.size() + i] = -INFINITY; }
       std::copy(cthr.begin(), cthr.end(), cthr_pad.begin() + kCthrPad);
+      std::vector<double> thr_pad(thr.size() + 2 * kCthrPad);      // "thr <= R": -Inf below (holds), +Inf above (does not)
+      for (int i = 0; i < kCthrPad; ++i) { thr_pad[i] = -INFINITY; thr_pad[kCthrPad + thr.size() + i] = INFINITY; }
+      std::copy(thr.begin(), thr.end(), thr_pad.begin() + kCthrPad);
+      {
+        // #{thr <= R} ~ floor(position of R on the log-spaced grid + 0.49), log2 R ~ hi32(R) / 2^20 - 1023 + 0.043
+        const double scale = (double)(nr - 1) / (std::log10(r[nr - 1]) - std::log10(r[0]));
+        const double l2 = 0.30102999566398120 * scale;
+        P.rg_b = l2 / 1048576.0;
+        P.rg_a = -std::log10(r[0]) * scale - (1023.0 - 0.043) * l2 + 0.49;
+      }
       double *dr, *dthr, *dcthr, *dWt, *dHPH, *dSD, *dRS2, *dG = nullptr, *dvm = nullptr;
-      if ((rc = pl->arena.upload(&dr, r)) || (rc = pl->arena.upload(&dthr, thr)) || (rc = pl->arena.upload(&dWt, Wtab)) ||
+      if ((rc = pl->arena.upload(&dr, r)) || (rc = pl->arena.upload(&dthr, thr_pad)) || (rc = pl->arena.upload(&dWt, Wtab)) ||
           (rc = pl->arena.upload(&dHPH, HPH)) || (rc = pl->arena.upload(&dcthr, cthr_pad)) ||
           (rc = pl->arena.upload(&dSD, SDt)) || (rc = pl->arena.upload(&dRS2, RS2t)))
         return cleanup(rc);
       P.cthr = dcthr + kCthrPad; P.SDtab = dSD; P.RS2tab = dRS2;
       if (tb.PG && ((rc = pl->arena.upload(&dG, Gtab)) || (rc = pl->arena.upload(&dvm, vmtab)))) return cleanup(rc);
-      P.r = dr; P.thr = dthr; P.Wtab = dWt; P.HPHtab = dHPH; P.Gtab = dG; P.vmtab = dvm;
+      P.r = dr; P.thr = dthr + kCthrPad; P.Wtab = dWt; P.HPHtab = dHPH; P.Gtab = dG; P.vmtab = dvm;
     } else {
       ho = 0; po = 0;
       for (int i = 0; i < M; ++i) {

@@ -35,7 +35,9 @@ struct DevProblem {
   const double* xn;              // [NP][S]
   // IHGP tables
   const double* r;               // [nr]
-  const double* thr;             // [nr-1] decision thresholds of the nearest-neighbour search
+  const double* thr;             // [nr-1] decision thresholds of the nearest-neighbour search; kCthrPad sentinels
+                                 // (-Inf below index 0, +Inf above nr-2) surround the array
+  double rg_a, rg_b;             // row guess from the high word of R: floor(rg_a + rg_b * hi32(R)) (log-spaced grid)
   const double* Wtab;            // [M][nr+1][BM]  PP*h'  (row nr: Pinf)
   const double* HPHtab;          // [M][nr+1]      h*PP*h'
   const double* Gtab;            // [M][nr][BM*BM] smoother gain

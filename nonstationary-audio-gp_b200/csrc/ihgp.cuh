@@ -144,39 +144,34 @@ ihgp_adf_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict
 }
 
 // ------------------------------------------------------ affine scan elements
-// ind = #{i : thr[i] <= R} (thr ascending, nthr entries), trying a 6-entry window around
-// `hint` first: consecutive time steps have similar R, and one round trip to L1 replaces the
-// eight dependent ones of a binary search.
-__device__ __forceinline__ int count_le_window(const double* __restrict__ thr, int nthr, double R, int hint) {
-  const int last = nthr - 1;
-  const int h = min(max(hint, 0), last);
-  const int lo = max(h - 3, 0), hi = min(h + 2, last);
+// ind = #{i : thr[i] <= R} (thr ascending, nthr entries).  The row is guessed from the bits of R (the high word of a
+// double is a piecewise-linear log2, the grid is log-spaced: the guess is within one row) and confirmed by counting
+// six thresholds around it, loaded at once -- one round trip to L1 instead of the eight dependent ones of a binary
+// search, and no dependence on the previous step's row (sites of neighbouring steps can differ by decades early in
+// EP).  thr carries kCthrPad sentinels on either side; a grid that is not log-spaced only costs the binary search.
+__device__ __forceinline__ int count_le_guess(const DevProblem& P, int nthr, double R) {
+  const double* __restrict__ thr = P.thr;
+  const int guess = min(max(__double2int_rd(fma((double)__double2hiint(R), P.rg_b, P.rg_a)), 0), nthr);
+  const int w0 = guess - 3;
   int cnt = 0;
-  bool first = false, end = false;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int i = min(lo + j, hi);
-    const bool le = thr[i] <= R;
-    cnt += (lo + j <= hi && le) ? 1 : 0;
-    if (j == 0) first = le;
-    end = le;
-  }
-  if ((lo == 0 || first) && (hi == last || !end)) return lo + cnt;
+  for (int j = 0; j < 6; ++j) cnt += (thr[w0 + j] <= R) ? 1 : 0;
+  if (cnt > 0 && cnt < 6) return w0 + cnt;
   return nearest_by_threshold(thr, nthr + 1, R);
 }
 
-__device__ __forceinline__ int lookup_filter_hint(const double* r, const double* thr, int nr, double R, int hint) {
+__device__ __forceinline__ int lookup_filter_hint(const DevProblem& P, double R) {
   if (!(R > 0.0)) return 0;
   if (isinf(R)) return 0;
-  if (R >= kLookupBig) return nearest_bruteforce(r, nr, R);
-  return count_le_window(thr, nr - 1, R, hint);
+  if (R >= kLookupBig) return nearest_bruteforce(P.r, P.nr, R);
+  return count_le_guess(P, P.nr - 1, R);
 }
 
-__device__ __forceinline__ int lookup_smoother_hint(const double* r, const double* thr, int nr, double R, int hint) {
-  if (isinf(R)) return nr - 1;
+__device__ __forceinline__ int lookup_smoother_hint(const DevProblem& P, double R) {
+  if (isinf(R)) return P.nr - 1;
   if (!(R > 0.0)) return 0;
-  if (R >= kLookupBig) return nearest_bruteforce(r, nr, R);
-  return count_le_window(thr, nr - 1, R, hint);
+  if (R >= kLookupBig) return nearest_bruteforce(P.r, P.nr, R);
+  return count_le_guess(P, P.nr - 1, R);
 }
 
 template <int BM>
@@ -269,9 +264,9 @@ template <int BM>
 struct FilterElem : AffineElemBase<BM> {
   using Map = Affine<BM>;
   using State = MeanState<BM>;
-  const DevProblem& P; const DevState& St; int n, off, b, hint;
+  const DevProblem& P; const DevState& St; int n, off, b;
   double A[BM * BM], hA[BM];
-  __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), hint(0) {
+  __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
@@ -294,8 +289,7 @@ struct FilterElem : AffineElemBase<BM> {
     if (k > 0) {
       const double ttp = fmax(St.ttau[(k - 1) * M + n], 0.0);
       const double Rp = (ttp == 0.0) ? INFINITY : St.R[(k - 1) * M + n];
-      idx = lookup_filter_hint(P.r, P.thr, nr, Rp, hint);
-      hint = idx;
+      idx = lookup_filter_hint(P, Rp);
     }
     const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BM;
     const double HPH = P.HPHtab[(size_t)n * (nr + 1) + idx];
@@ -335,10 +329,10 @@ template <int BM>
 struct SmootherElem : AffineElemBase<BM> {
   using Map = Affine<BM>;
   using State = MeanState<BM>;
-  const DevProblem& P; const DevState& St; int n, off, b, hint;
+  const DevProblem& P; const DevState& St; int n, off, b;
   double A[BM * BM], hv[BM];
   double mdM;
-  __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), hint(0), mdM(0.0) {
+  __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), mdM(0.0) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
@@ -347,8 +341,7 @@ struct SmootherElem : AffineElemBase<BM> {
   }
   __device__ __forceinline__ void get_impl(long long k, Map& e, bool commit) {
     const int M = P.M, nr = P.nr;
-    const int idx = lookup_smoother_hint(P.r, P.thr, nr, St.R[k * M + n], hint);
-    hint = idx;
+    const int idx = lookup_smoother_hint(P, St.R[k * M + n]);
     const double* G = P.Gtab + ((size_t)n * nr + idx) * BM * BM;
     double ms[BM], t[BM];
 #pragma unroll
@@ -446,7 +439,7 @@ site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
     if (FULL) {
       vm = St.V[k * M + n];
     } else {
-      const int idx = lookup_smoother(P.r, P.thr, nr, St.R[k * M + n]);
+      const int idx = lookup_smoother_hint(P, St.R[k * M + n]);
       vm = P.vmtab[(size_t)n * nr + idx];
     }
     const double mm = St.E[k * M + n];
