@@ -794,12 +794,19 @@ template <class Elem>
 int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags) {
   a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.flags = flags; a.nprev = 0;
   a.CH = scan_ch(pl, Elem::kMapDoubles);
-  // registers: a CTA tile of 32*CH threads must fit the SM's 64 K registers
-  cudaFuncAttributes f1, f3;
-  CU(cudaFuncGetAttributes(&f1, scan_reduce_kernel<Elem>));
-  CU(cudaFuncGetAttributes(&f3, scan_apply_kernel<Elem>));
-  const int regs = std::max(f1.numRegs, f3.numRegs);
-  while (a.CH > 1 && pl->M * a.CH * regs > 65536) a.CH >>= 1;
+  // a CTA tile of M*CH threads must fit an SM (registers, shared memory): ask the occupancy calculator
+  auto fits = [&](int ch) {
+    const size_t sm1 = (size_t)ch * pl->M * Elem::kMapDoubles * sizeof(double);
+    const size_t sm3 = (size_t)ch * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
+    if (sm1 > 48 * 1024) cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    if (sm3 > 48 * 1024) cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+    int n1 = 0, n3 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, scan_reduce_kernel<Elem>, pl->M * ch, sm1) != cudaSuccess) n1 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, scan_apply_kernel<Elem>, pl->M * ch, sm3) != cudaSuccess) n3 = 0;
+    cudaGetLastError();
+    return n1 >= 1 && n3 >= 1;
+  };
+  while (a.CH > 1 && !fits(a.CH)) a.CH >>= 1;
   return NSAGP_OK;
 }
 

@@ -27,6 +27,7 @@ CASES = [
     (6, 3, 400, "exp", "matern52", "precalc", 9, 1.0, 0.75, 3, True),        # missing-data gaps
     (5, 2, 260, "matern52", "matern32", "power", 7, 0.0, 0.5, 2, False),     # 6x6 subband blocks
     (3, 2, 200, "matern72", "exp", "power", 5, 0.0, 1.0, 2, False),          # 8x8 and 1x1 blocks
+    (16, 3, 200, "exp", "matern52", "precalc", 9, 1.0, 0.75, 2, False),      # C3's own shape (M = 19 lanes per chunk in the scans)
 ]
 
 
