@@ -226,3 +226,26 @@ def test_nlz_batch_sharding_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and o.strip().endswith("ok"), o
+
+
+def test_row_guess_from_float_bits_is_within_the_lookup_window():
+    """The kernels guess the table row of R (or of ttau = 1/R) from the high 32 bits of the double -- a piecewise-linear
+    log2 -- and confirm it by counting six thresholds, rows guess-3 .. guess+2 (csrc/ihgp.cuh: count_le_guess,
+    csrc/adfcta.cuh: lookup_by_ttau; coefficients: api.cu rg_a / rg_b, make_ttau_guess).  For the reference's grid
+    r = logspace(-2, 4, 200) the guess must land within two rows of the nearest-neighbour answer for every R, inside and
+    outside the grid, or the kernels fall back to a binary search on every look-up (correct, but slow)."""
+    nr = 200
+    r = np.logspace(-2, 4, nr)
+    scale = (nr - 1) / (np.log10(r[-1]) - np.log10(r[0]))
+    l2 = 0.30102999566398120 * scale
+    R = np.concatenate([np.logspace(-4, 6, 200001), r, r * (1 + 1e-12), r * (1 - 1e-12), 0.5 * (r[1:] + r[:-1])])
+    truth = np.argmin(np.abs(r[None, :] - R[:, None]), axis=1)               # [~, ind] = min(abs(r - R)), first on ties
+    hi = (R.view(np.uint64) >> np.uint64(32)).astype(np.float64)
+    guess_R = np.clip(np.floor(-np.log10(r[0]) * scale - (1023.0 - 0.043) * l2 + 0.49 + hi * (l2 / 1048576.0)), 0, nr - 1)
+    assert np.max(np.abs(guess_R - truth)) <= 2
+    tt = 1.0 / R
+    hit = (tt.view(np.uint64) >> np.uint64(32)).astype(np.float64)
+    guess_t = np.clip(np.floor(-np.log10(r[0]) * scale + (1023.0 - 0.043) * l2 + 0.49 - hit * (l2 / 1048576.0)), 0, nr - 1)
+    assert np.max(np.abs(guess_t - truth)) <= 2
+    # and it is usually exact or one off: the six-entry window is not wasteful
+    assert np.mean(np.abs(guess_R - truth) <= 1) > 0.999 and np.mean(np.abs(guess_t - truth) <= 1) > 0.999
