@@ -291,7 +291,8 @@ giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
   double* sA = P + (size_t)n * n;            // [M*BM*BM]
   double* sQ = sA + M * BM * BM;
   double* sh = sQ + M * BM * BM;             // [M*BM]
-  double* sW = sh + M * BM;                  // [D*N]
+  double* shA = sh + M * BM;                 // [M*BM]  h*A
+  double* sW = shA + M * BM;                 // [D*N]
   double* mbuf = sW + D * N;                 // [2][n]
   double* JH = mbuf + 2 * n;                 // [n]
   double* PJ = JH + n;                       // [n]
@@ -310,7 +311,13 @@ giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
   if (kStaged) for (int i = tid; i < ps_stride; i += nth) Pstage[i] = 0.0;
   for (int i = tid; i < n * n; i += nth) P[i] = a.Pinf[i];                     // :168
   for (int i = tid; i < M * BM * BM; i += nth) { sA[i] = a.A[i]; sQ[i] = a.Q[i]; }
-  for (int i = tid; i < M * BM; i += nth) sh[i] = a.h[i];
+  for (int i = tid; i < M * BM; i += nth) {
+    sh[i] = a.h[i];
+    const int bq = i / BM, cq = i % BM;
+    double acc = 0.0;
+    for (int r = 0; r < BM; ++r) acc = fma(a.h[bq * BM + r], a.A[bq * BM * BM + r + cq * BM], acc);
+    shA[i] = acc;
+  }
   for (int i = tid; i < D * N; i += nth) sW[i] = a.W[i];
   for (int i = tid; i < n; i += nth) { mbuf[i] = a.m_io[i]; Kv[i] = 0.0; Ks[i] = 0.0; }
   for (int b = tid; b <= M; b += nth) s_off[b] = a.off[b];
@@ -365,22 +372,24 @@ giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
         const bool pred_now = it == 0 && do_pred && !last;
         const double* mc = pred_now ? m2 : m;
         if (it > 0) bar_mean();                                                // phase D's mean is complete
-        // B1: every latent's thread predicts its own block of the mean, f = H m; warp 0 reduces z'W over the
-        // subbands; the modulators' threads evaluate the link and its derivative
+        // B1: f = H (A m) = (H A) m straight from the previous mean (hA is precomputed: no wait for the predicted
+        // mean), the predicted mean row by row on the state threads, z'W reduced over the subbands by warp 0, the
+        // modulators' threads evaluate the link and its derivative
+        const double* hsel = pred_now ? shA : sh;
+        const double* msrc = pred_now ? m : mc;
         double f = 0.0;
-        if (tid < M) {
+        if (tid < M && (upd || pred_now)) {
           const int o = s_off[tid], nb = s_off[tid + 1] - o;
-          if (pred_now) {
-            for (int r = 0; r < nb; ++r) {
-              double mv = 0.0;
-              for (int c = 0; c < nb; ++c) mv = fma(sA[tid * BM * BM + r + c * BM], m[o + c], mv);
-              m2[o + r] = mv;
-              f = fma(sh[tid * BM + r], mv, f);
-            }
-          } else if (upd) {
-            for (int c = 0; c < nb; ++c) f = fma(sh[tid * BM + c], mc[o + c], f);
-          }
+#pragma unroll 1
+          for (int c = 0; c < nb; ++c) f = fma(hsel[tid * BM + c], msrc[o + c], f);
           fv[tid] = f;
+        }
+        if (pred_now && tid < n) {
+          const int nb = s_off[my_b + 1] - my_o;
+          double mv = 0.0;
+#pragma unroll 1
+          for (int c = 0; c < nb; ++c) mv = fma(sA[my_b * BM * BM + (tid - my_o) + c * BM], m[my_o + c], mv);
+          m2[tid] = mv;
         }
         if (upd) {
           if (warp == 0) {
@@ -388,20 +397,22 @@ giekf_filter2_kernel(const EkfArgs* __restrict__ argv, int l_iter, int energy) {
             const int d2 = lane + 32;
             if (d2 < D) {
               const int o = s_off[d2], nb = s_off[d2 + 1] - o;
-              for (int r = 0; r < nb; ++r) {
-                double mv = 0.0;
-                if (pred_now) { for (int c = 0; c < nb; ++c) mv = fma(sA[d2 * BM * BM + r + c * BM], m[o + c], mv); }
-                else mv = mc[o + r];
-                f2 = fma(sh[d2 * BM + r], mv, f2);
-              }
+#pragma unroll 1
+              for (int c = 0; c < nb; ++c) f2 = fma(hsel[d2 * BM + c], msrc[o + c], f2);
             }
             const double f1 = lane < D ? f : 0.0;
-            for (int j = 0; j < N; ++j) {
-              double zw = lane < D ? f1 * sW[lane * N + j] : 0.0;
-              if (d2 < D) zw = fma(f2, sW[d2 * N + j], zw);
+#pragma unroll 1
+            for (int j = 0; j < N; j += 2) {                                   // two modulators per round: independent chains
+              const bool two = j + 1 < N;
+              double za = lane < D ? f1 * sW[lane * N + j] : 0.0;
+              double zb = (two && lane < D) ? f1 * sW[lane * N + j + 1] : 0.0;
+              if (d2 < D) { za = fma(f2, sW[d2 * N + j], za); if (two) zb = fma(f2, sW[d2 * N + j + 1], zb); }
 #pragma unroll
-              for (int o = 16; o >= 1; o >>= 1) zw += __shfl_xor_sync(0xffffffffu, zw, o);
-              if (lane == 0) zWv[j] = zw;
+              for (int o = 16; o >= 1; o >>= 1) {
+                za += __shfl_xor_sync(0xffffffffu, za, o);
+                zb += __shfl_xor_sync(0xffffffffu, zb, o);
+              }
+              if (lane == 0) { zWv[j] = za; if (two) zWv[j + 1] = zb; }
             }
           }
           if (tid >= D && tid < M) {

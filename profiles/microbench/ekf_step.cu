@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
   a.sigma2 = 1e-2; a.y = dy; a.MS = dMS; a.PS = dPS; a.ps_stride = ps_stride; a.m_io = dm; a.edata = de; a.status = dstat;
   cudaMalloc(&dargs, sizeof(a)); cudaMemcpy(dargs, &a, sizeof(a), cudaMemcpyHostToDevice);
   const int staged = 1;
-  const size_t sm = ((staged ? ps_stride : 0) + (size_t)n * n + 2 * M * BM * BM + M * BM + D * N + 6 * n + 64 + M + 3 * N + D + 16) * 8;
+  const size_t sm = ((staged ? ps_stride : 0) + (size_t)n * n + 2 * M * BM * BM + 2 * M * BM + D * N + 6 * n + 64 + M + 3 * N + D + 16) * 8;
   auto kf = giekf_filter2_kernel<BZ, BG, BM>;
   cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
