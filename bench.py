@@ -50,6 +50,13 @@ def damping(itts):
     return np.linspace(0.01, 0.1, itts)
 
 
+def config_dict(T, itts):
+    """The `config` object of the JSON line -- identical for the GPU arm and the reference arm."""
+    return {"workload": WORKLOAD if (T == T_FULL and itts == EP_ITTS) else "C2 shape with T=%d ep_itts=%d (non-default)" % (T, itts),
+            "T": T, "ep_itts": itts, "signals_per_gpu": 1, "l2": "flushed between timed runs (256 MiB write)",
+            "step": "one full EP run = ep_itts filter+smoother sweeps"}
+
+
 def make_signal(nsagp, seed, T):
     rng = np.random.default_rng(seed)
     hyp = nsagp.synth.speech_hypers(D, N, rng)
@@ -66,6 +73,50 @@ def host_setup(nsagp, hyp):
     mdl = nsagp.to_block_model(A, Q, H, Pinf, D, N)
     tabs = nsagp.tables.build_tables(mdl, want_smoother=True)
     return mdl, tabs
+
+
+def prefix_check(nsagp, seed=2026, Tp=2000, itts=EP_ITTS, hyp=None, y=None):
+    """The metric's second half ("lZ rel. error"): the product path against the C restatement of the reference
+    (oracle/c/nsagp_oracle.c, the checker -- never the thing measured) on the first Tp samples of the benched signal,
+    same model, same EP schedule.  Runs OUTSIDE every timed region.  Kernel parity is measured on the oracle's own
+    steady-state tables (SciPy Riccati solver); `*_native_tables` additionally swaps in the library's own table
+    routine (what the timed runs use), whose solutions differ from SciPy's by ~1e-10 and can flip a
+    nearest-neighbour table look-up."""
+    from oracle import c_oracle, cubature as ocub, ihgp_ep, ssmodel as oss
+    lib_mod = nsagp._lib
+    if hyp is None:
+        hyp, y = make_signal(nsagp, seed, T_FULL)
+    yp = np.ascontiguousarray(y[:Tp])
+    damp = damping(itts)
+    lik_param, p1, p2, W = oss.unpack_log(hyp.pack_log(), 1, D, N)
+    ss = lambda x, a, b, k1, k2: oss.ss_modulators_nmf(a, b, k1, k2)
+    A, Q, H, Pinf = ihgp_ep._model(lik_param, p1, p2, ss, np.arange(1.0, Tp + 1), K1, K2)
+    wo, xo = ocub.utp_ws(P_CUB, N)
+    ref = c_oracle.IhgpProblem(A, H, Pinf, ihgp_ep.ihgp_setup(A, Q, H), 1, lik_param, SHIFT, W, wo, xo, ALPHA, damp,
+                               itts).predict(yp)
+    F, L_, Qc, Hh, Pi = nsagp.ss_modulators_nmf(hyp.w_sub(), hyp.w_mod(), K1, K2)[:5]
+    F, L_, Hh, Pi = nsagp.ssmodel.balance(F, L_, Hh, Pi)
+    Ad, Qd = nsagp.lti_disc(F, L_, Qc, 1.0)
+    mdl = nsagp.to_block_model(Ad, (Qd + Qd.T) / 2, Hh, Pi, D, N)
+    wn, xn = nsagp.utp_ws(P_CUB, N)
+    mom = nsagp.likModulatorPreCalcwn(nsagp.Softplus(SHIFT), wn, xn)
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+    out = {"prefix_steps": Tp, "ep_itts": itts, "oracle": "oracle/c/nsagp_oracle.c (plain-C restatement; parity unpinned: "
+           "the reference is MATLAB and ships no golden vectors)"}
+    for native in (False, True):
+        tabs = nsagp.tables.build_tables(mdl, want_smoother=True, native=native)
+        with nsagp.Plan(lib_mod.KIND_IHGP, [mdl], [(mom, np.log([hyp.w_lik]), hyp.W)], ALPHA, damp, itts, yp[None, :],
+                        lib_mod.MODE_PREDICT, tables=[tabs]) as plan:
+            plan.run()
+            got = plan.fetch(0, ("Eft", "nlZ", "ttau", "MS"))
+        sfx = "_native_tables" if native else ""
+        out["lZ_rel_err" + sfx] = float(np.max(np.abs(got["nlZ"] - ref["nlZ"]) / np.abs(ref["nlZ"])))
+        out["Eft_rel_err" + sfx] = rel(got["Eft"], ref["Eft"])
+        if not native:
+            out["lZ_rel_err_first_sweep"] = float(abs(got["nlZ"][0] - ref["nlZ"][0]) / abs(ref["nlZ"][0]))
+            out["ttau_rel_err"] = rel(got["ttau"], ref["ttau"])
+            out["MS_rel_err"] = rel(got["MS"], ref["MS"])
+    return out
 
 
 class ClockSampler:
@@ -155,21 +206,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # The workload is ONE signal per GPU (weak scaling: `gpus` independent signals).  The reference's
-    # loop is serial in time (no parfor, n = 41 matrices too small for BLAS threads), so
-    # one signal can use one host core; `gpus` signals use `gpus` cores.
-    cores = max(1, min(os.cpu_count() or 1, args.gpus))
-    T_sample, itts = 1000, EP_ITTS
+    # The reference's loop is serial in time (no parfor; its n = 41 matrices are too small for BLAS
+    # threads), so ONE signal can use one host core.  "All the host threads it can use" is therefore one independent
+    # signal per core; the value is the box's aggregate throughput over those signals, per-core figure in `sample`.
+    cores = max(1, os.cpu_count() or 1)
+    T_sample, itts = args.ref_T, args.ep_itts
     value, per_step = cpu_arm(args.steps, args.warmup, T_sample, itts, cores)
-    sample = ("%d independent signal(s), one per host core (the reference loop is serial per signal), T=%d of the "
-              "workload's 100000 steps, ep_itts=%d per step; plain-C port of matlab/ihgp_ep_modulator_nmf.m "
-              "(oracle/c/nsagp_oracle.c), model/table setup untimed" % (cores, T_sample, itts))
+    sample = ("bounded sample of the workload: %d independent signals (one per host core; the reference loop is serial per "
+              "signal), the first T=%d of the workload's %d samples each, the workload's full EP schedule (ep_itts=%d) per step; "
+              "plain-C port of matlab/ihgp_ep_modulator_nmf.m (oracle/c/nsagp_oracle.c, same dense operations; the reference is "
+              "MATLAB and neither MATLAB nor Octave exists here or on the GPU box); per-step cost is independent of T; "
+              "%.0f time-steps/s per core; model/table setup untimed as on the GPU side" % (cores, T_sample, args.T, itts, value / cores))
     line = {"impl": "reference", "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value,
             "unit": "time-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "the reference is MATLAB; MATLAB/Octave are absent here and on the "
-                       "GPU box, so its loop restated in C (same dense operations) is timed on the host cores"},
+            "dtype": "f64", "data": "synthetic", "config": config_dict(args.T, itts),
             "cpu_baseline": {"value": value, "unit": "time-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "time-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -313,10 +364,7 @@ def run_gpu(args):
             "metric": "EP filter+smoother time-steps/sec (FP64)", "value": value, "unit": "time-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (T == T_FULL and itts == EP_ITTS) else
-                       "C2 shape with T=%d ep_itts=%d (non-default)" % (T, itts),
-                       "T": T, "ep_itts": itts, "signals_per_gpu": 1, "l2": "flushed between timed runs (256 MiB write)",
-                       "step": "one full EP run = ep_itts filter+smoother sweeps"},
+            "config": config_dict(T, itts),
             "e2e": {"value": e2e_value, "unit": "time-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "call": "nsagp_ep_ihgp (C ABI, host buffers)"},
             "gpu_launches": launches,
@@ -331,6 +379,9 @@ def run_gpu(args):
                          "cycles_per_time_step": adf_ms * 1e-3 * sm_hz / T if adf_ms > 0 else None,
                          "whole_run_GBps": sweep_bytes / (dev_ms / args.steps * 1e-3) / 1e9},
             "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+            "ep_itts_1": {"note": "what the reference's training runs (experiments/train_model.m:59-60): ONE sweep = the "
+                                  "sequential first filter pass; time-steps/s of that pass alone on one signal",
+                          "steps_per_s": world * T / (adf_ms * 1e-3) if adf_ms > 0 else None},
             "adf_only_steps_per_s": T / (adf_ms * 1e-3) if adf_ms > 0 else None,
             "setup_s": {"host_model_and_dare_tables": setup_s, "signal_generation": gen_s},
             "check": {"nlZ_first": float(chk["nlZ"][0]), "nlZ_last": float(chk["nlZ"][-1]), "n_negcav": chk["n_negcav"]},
@@ -343,6 +394,33 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": "time-steps/s", "cores": cores, "kind": "port",
                                     "sample": "plain-C port of matlab/ihgp_ep_modulator_nmf.m (oracle/c/nsagp_oracle.c, same dense "
                                               "operations), same model, T=%d ep_itts=%d, 1 core (%.1f s)" % (Tc, ic, per)}
+    # ---- the other BASELINE configurations (strong-scaling workloads; all ranks take part) ----------------------
+    extras = {}
+    if not args.no_extras:
+        import bench_workloads as bw
+        ctx = bw.Ctx(nsagp, torch, dist, rank, world, local_rank)
+        t_ex = time.perf_counter()
+        for name, fn in (("c3_one_signal_500k", lambda: bw.one_signal_chunked(ctx, "full", 500000, 20, 7, label="C3")),
+                         ("ihgp_one_signal_10M", lambda: bw.one_signal_chunked(ctx, "ihgp", args.long_T, 20, 9, reps=1, warm=1,
+                                                                               exact=(world == 1), label="north_star 10M")),
+                         ("c5_batch_256_clips", lambda: bw.c5_batch(ctx)),
+                         ("c4_giekf", lambda: bw.c4_giekf(ctx))):
+            try:
+                extras[name] = fn()
+            except Exception as e:                       # an extra workload must never take the headline line down
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                if dist is not None:
+                    raise
+            L.nsagp_release_cache()
+        extras["wall_s"] = time.perf_counter() - t_ex
+    if rank == 0:
+        if extras:
+            line["extras"] = extras
+        if not args.no_parity:
+            try:
+                line["lZ_rel_err"] = prefix_check(nsagp, hyp=hyp, y=y, Tp=min(2000, T), itts=itts)
+            except Exception as e:
+                line["lZ_rel_err"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -357,6 +435,10 @@ def main():
     ap.add_argument("--T", type=int, default=T_FULL)
     ap.add_argument("--ep-itts", dest="ep_itts", type=int, default=EP_ITTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (extras object)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the lZ rel. error check against the oracle")
+    ap.add_argument("--long-T", dest="long_T", type=int, default=10000000)
+    ap.add_argument("--ref-T", dest="ref_T", type=int, default=2000, help="reference arm: samples per signal per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

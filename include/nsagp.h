@@ -257,6 +257,30 @@ int nsagp_plan_destroy(nsagp_plan* plan);
 int nsagp_plan_set_range(nsagp_plan* plan, int64_t t0, int64_t t1);
 int nsagp_plan_stage(nsagp_plan* plan, int32_t stage, double x, int64_t k, const double* in, int64_t n_in,
                      double* out, int64_t n_out);
+/* The same with a DEVICE-SIDE carry exchange (csrc/comm.cuh): every rank owns a mailbox in its HBM that its peers
+ * write through NVLink peer access; one small kernel per pass posts the rank's record (scan aggregate, one-step site
+ * halo, end-point mean, lZ partial sum) into every peer's mailbox and waits for theirs.  nsagp_plan_run_chunked
+ * enqueues the rank's whole EP schedule (ihgp_ep_modulator_nmf.m:223-454 / gf_ep_modulator_nmf.m:113-283) without
+ * a host synchronisation.  Set-up: nsagp_comm_create on every rank, exchange the 64-byte IPC handles
+ * (nsagp_comm_export) out of band -- chunked.py uses torch.distributed once -- then nsagp_comm_connect.  Ranks that
+ * are threads of one process pass device addresses instead of handles. */
+typedef struct nsagp_comm nsagp_comm;
+int nsagp_comm_create(nsagp_comm** out, int32_t rank, int32_t world, int64_t slot_doubles);
+int nsagp_comm_export(nsagp_comm* comm, void* handle64, uint64_t* local_ptr);
+int nsagp_comm_connect(nsagp_comm* comm, const void* handles, const uint64_t* ptrs);
+int nsagp_comm_destroy(nsagp_comm* comm);
+int64_t nsagp_plan_comm_slot_doubles(nsagp_plan* plan);
+int nsagp_plan_run_chunked(nsagp_plan* plan, nsagp_comm* comm);
+/* Opt-in, approximate, error-reported: the first filter pass (ADF; ihgp_ep_modulator_nmf.m:233-310,
+ * gf_ep_modulator_nmf.m:126-184) is a nonlinear recurrence in time.  With chunks > 1 it is run as `chunks` time
+ * chunks in parallel (one CTA each), every chunk starting `burnin` steps early from the stationary prior and
+ * discarding the burn-in; with nsagp_plan_run_chunked every rank does so over its own range only.  The filter
+ * forgets its start at the rate of the slowest latent, so the deviation from the exact pass decays with `burnin`;
+ * nsagp_plan_adf_mismatch returns the MEASURED disagreement at the chunk boundaries of the last run:
+ * out2[0] = max |mean a chunk holds after its burn-in - mean the preceding chunk stored for that step|,
+ * out2[1] = max |stored mean| there.  chunks <= 1: the exact sequential pass (default). */
+int nsagp_plan_set_adf_parallel(nsagp_plan* plan, int32_t chunks, int64_t burnin);
+int nsagp_plan_adf_mismatch(nsagp_plan* plan, double* out2);
 /* Device time (ms, CUDA events on the launch stream) of the phases of the last
  * nsagp_plan_run: [0] total, [1] ADF filter pass, [2] fixed-site filter passes,
  * [3] smoother passes, [4] site-update passes.  Returns the number written. */

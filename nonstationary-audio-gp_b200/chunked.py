@@ -205,6 +205,82 @@ def run_full_chunked(plan, comm, ep_damping):
     return ranges
 
 
+# ------------------------------------------------------------------- device-side carry exchange
+class DeviceComm:
+    """Mailbox exchange over NVLink peer access (csrc/comm.cuh; C ABI nsagp_comm_*): after a one-time set-up the
+    ranks never meet on the host again during an EP run.  ``connect_torch`` exchanges the CUDA IPC handles of the
+    mailboxes once through torch.distributed (one process per GPU); ``connect_threads`` wires emulated ranks that
+    are threads of one process (one GPU) by device address."""
+
+    def __init__(self, rank, world, slot_doubles):
+        self.rank, self.world = int(rank), int(world)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().nsagp_comm_create(C.byref(self._h), self.rank, self.world, int(slot_doubles)))
+
+    def export(self):
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_uint64()
+        _lib.check(_lib.lib().nsagp_comm_export(self._h, handle, C.byref(ptr)))
+        return bytes(handle), int(ptr.value)
+
+    def connect_handles(self, handles):
+        buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        _lib.check(_lib.lib().nsagp_comm_connect(self._h, buf, None))
+        return self
+
+    def connect_ptrs(self, ptrs):
+        arr = (C.c_uint64 * self.world)(*[int(p) for p in ptrs])
+        _lib.check(_lib.lib().nsagp_comm_connect(self._h, None, arr))
+        return self
+
+    @classmethod
+    def connect_torch(cls, plan, group=None):
+        """One process per GPU: all ranks call this with their (identically shaped) plan."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        cm = cls(rank, world, _lib.lib().nsagp_plan_comm_slot_doubles(plan._h))
+        handle, _ = cm.export()
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        if world > 1:
+            cm.connect_handles(handles)
+        return cm
+
+    @classmethod
+    def connect_threads(cls, plans):
+        """Emulated ranks inside one process: one comm per plan, wired by device address."""
+        world = len(plans)
+        cms = [cls(r, world, _lib.lib().nsagp_plan_comm_slot_doubles(pl._h)) for r, pl in enumerate(plans)]
+        ptrs = [cm.export()[1] for cm in cms]
+        if world > 1:
+            for cm in cms:
+                cm.connect_ptrs(ptrs)
+        return cms
+
+    def close(self):
+        if self._h:
+            _lib.lib().nsagp_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_chunked_device(plan, dcomm):
+    """The whole EP schedule of a predict-mode plan (either kind, B = 1), frozen-site passes sharded over the ranks
+    of ``dcomm``, carries exchanged on the device.  One C call, no host synchronisation inside.  With
+    ``plan.set_adf_parallel(chunks, burnin)`` the first filter pass is sharded too (approximate, error reported by
+    ``plan.adf_mismatch()``); otherwise it runs replicated and exact on every rank."""
+    ranges = split_ranges(plan.T, dcomm.world)
+    t0, t1 = ranges[dcomm.rank]
+    _lib.check(_lib.lib().nsagp_plan_set_range(plan._h, t0, t1))
+    _lib.check(_lib.lib().nsagp_plan_run_chunked(plan._h, dcomm._h))
+    return ranges
+
+
 def gather_outputs(plan, comm, ranges, names=("Eft", "Varft", "lb", "ub")):
     """Assemble the time-indexed outputs from every rank's own range; every rank gets the result."""
     res = plan.fetch(0, tuple(names))

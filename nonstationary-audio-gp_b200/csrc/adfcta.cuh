@@ -86,6 +86,51 @@ struct AdfSmem {
   }
 };
 
+// Parallel-in-time ADF with burn-in overlap (opt-in, approximate, error-reported).  The window
+// [w0, w1) is cut into chunks of chunk_len steps, one CTA (blockIdx.y) per chunk.  A chunk that does not start at
+// step 0 starts `burn` steps early from the stationary prior (m = 0, P = Pinf / the Pinf table row), runs the
+// reference's literal recursion through the burn-in WITHOUT storing anything, and stores from its own first step
+// on.  The filter forgets its initial state at the rate of the slowest latent, so the deviation from
+// the exact sequential pass decays with `burn`; it is measured, not assumed: the state a chunk holds at the end of
+// its burn-in is recorded in bstate [chunk][n] and compared with what the preceding chunk stored for that step.
+// Cold start only (old sites are zero, as in every call of the reference): the burn-in never reads the site arrays,
+// which the preceding chunk is writing at that moment.  chunk_len = 0: the exact single pass.
+struct AdfPar {
+  long long w0, w1, chunk_len, burn;
+  double* bstate;
+};
+
+struct AdfWindow {
+  long long ks, kw0, kw1;       // first step executed, first step stored, end
+  bool chunked;
+  __device__ __forceinline__ AdfWindow(const AdfPar& par, long long k0, long long k1) {
+    chunked = par.chunk_len > 0;
+    if (!chunked) { ks = k0; kw0 = k0; kw1 = k1; return; }
+    kw0 = par.w0 + (long long)blockIdx.y * par.chunk_len;
+    kw1 = kw0 + par.chunk_len < par.w1 ? kw0 + par.chunk_len : par.w1;
+    ks = kw0 - par.burn > 0 ? kw0 - par.burn : 0;
+  }
+};
+
+// max over the chunk boundaries inside one launch of |state at the end of chunk c's burn-in - what chunk c-1 stored for
+// that step| and of |stored mean|: diag[0], diag[1] (bit patterns of non-negative doubles, atomicMax).
+__global__ void adf_mismatch_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, AdfPar par,
+                                    int nch, unsigned long long* __restrict__ diag) {
+  const DevProblem& P = probs[blockIdx.x];
+  const DevState& St = states[blockIdx.x];
+  double dm = 0.0, mm = 0.0;
+  for (int i = threadIdx.x; i < (nch - 1) * P.n; i += blockDim.x) {
+    const int c = 1 + i / P.n, j = i - (c - 1) * P.n;
+    const long long kw0 = par.w0 + (long long)c * par.chunk_len;
+    if (kw0 >= par.w1 || kw0 - par.burn <= 0) continue;       // (a chunk that reaches back to step 0 is exact)
+    const double ref = St.MS[(kw0 - 1) * P.n + j];
+    dm = fmax(dm, fabs(par.bstate[((size_t)blockIdx.x * nch + c) * P.n + j] - ref));
+    mm = fmax(mm, fabs(ref));
+  }
+  atomic_max_nonneg(diag, dm);
+  atomic_max_nonneg(diag + 1, mm);
+}
+
 // Loop of a moment thread: steps k0..k1-1, moments wherever the Kalman warp asks.
 template <int DPT, bool SINGLE>
 __device__ __forceinline__ void adf_moment_loop(const MomParams& mp, const double* __restrict__ yv, long long T,
@@ -115,8 +160,11 @@ __device__ __forceinline__ void adf_moment_loop(const MomParams& mp, const doubl
 template <int DPT, int BM, bool SINGLE, bool TABS>
 __global__ void __launch_bounds__(32 + kAdfMaxMomThreads)
 ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                    long long T, long long k0, long long k1, int mom_all, double ep_damp, int running) {
+                    long long T, long long k0_, long long k1_, int mom_all, double ep_damp, int running, AdfPar par) {
   constexpr int NVP = MomCta<DPT>::NVP;
+  const AdfWindow win(par, k0_, k1_);
+  const long long k0 = win.ks, k1 = win.kw1, kw0 = win.kw0;
+  if (kw0 >= k1) return;
   const DevProblem& P = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -171,6 +219,10 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     idx = nr;                                 // PP = Pinf at the first step (:246)
 #pragma unroll
     for (int i = 0; i < BM; ++i) m[i] = St.mcarry[n * BM + i];
+  } else if (win.chunked) {
+    idx = nr;                                 // burn-in from the stationary prior
+#pragma unroll
+    for (int i = 0; i < BM; ++i) m[i] = 0.0;
   } else {
 #pragma unroll
     for (int i = 0; i < BM; ++i) m[i] = (i < b) ? St.MS[(k0 - 1) * P.n + off + i] : 0.0;
@@ -179,9 +231,10 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     idx = lookup_filter(P.r, P.thr, nr, Rp);
   }
   // one-step-ahead loads of what does not depend on the recurrence
+  const bool ld_sites = !win.chunked;        // (chunked: cold start, old sites are zero and must not be read)
   double y_nx = St.y[k0];
-  double tt_nx = St.ttau[k0 * M + n];
-  double tn_nx = St.tnu[k0 * M + n];
+  double tt_nx = ld_sites ? St.ttau[k0 * M + n] : 0.0;
+  double tn_nx = ld_sites ? St.tnu[k0 * M + n] : 0.0;
   double R_nx = mom_all ? 0.0 : St.R[k0 * M + n];
   // outputs of the previous step, stored while the moment warps work
   bool pend = false, pend_mom = false;
@@ -226,11 +279,18 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     // ---- off the critical path: next step's loads, previous step's outputs ----
     if (k + 1 < k1) {
       y_nx = St.y[k + 1];
-      tt_nx = St.ttau[(k + 1) * M + n];
-      tn_nx = St.tnu[(k + 1) * M + n];
+      if (ld_sites) {
+        tt_nx = St.ttau[(k + 1) * M + n];
+        tn_nx = St.tnu[(k + 1) * M + n];
+      }
       if (!mom_all) R_nx = St.R[(k + 1) * M + n];
     }
-    if (pend) {
+    if (pend && pk < kw0) {
+      if (pk == kw0 - 1 && active && par.bstate) {                              // end of the burn-in: kept for the mismatch check
+#pragma unroll
+        for (int i = 0; i < BM; ++i) if (i < b) par.bstate[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * P.n + off + i] = m[i];
+      }
+    } else if (pend) {
       double Rk = p_R;
       if (pend_mom) {
         Rk = 1.0 / p_ttraw;                                                     // :269 (before the clamp)
@@ -310,8 +370,11 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
 template <int DPT, int BM, bool SINGLE>
 __global__ void __launch_bounds__(32 + kAdfMaxMomThreads)
 gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long T,
-                       long long k0, int mom_all, double ep_damp, int nlz, int store) {
+                       long long k0_, int mom_all, double ep_damp, int nlz, int store, AdfPar par) {
   constexpr int NVP = MomCta<DPT>::NVP;
+  const AdfWindow win(par, k0_, T);
+  const long long k0 = win.ks, k1 = win.kw1, kw0 = win.kw0;
+  if (kw0 >= k1) return;
   const DevProblem& P_ = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -331,7 +394,7 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
   const MomParams mp = make_mom_params(P_, P_.W, s_wn, s_xn);
 
   if (tid >= 32) {
-    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, T, mom_all, true, s_mom, tid - 32, nmt, nthreads);
+    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, k1, mom_all, true, s_mom, tid - 32, nmt, nthreads);
     return;
   }
 
@@ -359,21 +422,30 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
   const int off = P_.off[n];
   const int b = P_.off[n + 1] - off;
 
-  if (k0 > 0) {                                        // continue from the stored estimate of step k0-1
+  if (k0 > 0 && !win.chunked) {                        // continue from the stored estimate of step k0-1
+                                                       // (chunked: burn-in from the stationary prior (0, Pinf))
 #pragma unroll
     for (int i = 0; i < BM; ++i) m[i] = (i < b) ? St.MS[(k0 - 1) * P_.n + off + i] : 0.0;
     const double* src = St.PS + ((size_t)(k0 - 1) * M + n) * BM * BM;
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) P[i] = src[i];
   }
+  const bool ld_sites = !win.chunked;                  // (chunked: cold start, old sites are zero and must not be read)
   double y_nx = St.y[k0];
-  double tt_nx = St.ttau[k0 * M + n];
-  double tn_nx = St.tnu[k0 * M + n];
+  double tt_nx = ld_sites ? St.ttau[k0 * M + n] : 0.0;
+  double tn_nx = ld_sites ? St.tnu[k0 * M + n] : 0.0;
   bool pend = false, pend_obs = false, pend_mom = false;
   long long pk = 0;
   double p_tt = 0.0, p_tn = 0.0, p_Z = 1.0;
 
   auto flush = [&](bool last) {
+    if (pk < kw0) {                                                               // burn-in: nothing is stored
+      if (pk == kw0 - 1 && active && par.bstate) {
+#pragma unroll
+        for (int i = 0; i < BM; ++i) if (i < b) par.bstate[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * P_.n + off + i] = m[i];
+      }
+      return;
+    }
     // outputs of step pk: (m, P) still hold its posterior (:181-182)
     if (pend_mom) {
       if (lane == 0) St.lZ[pk] = log(pep * p_Z);
@@ -402,7 +474,7 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
     }
   };
 
-  for (long long k = k0; k < T; ++k) {
+  for (long long k = k0; k < k1; ++k) {
     const double y = y_nx;
     const double tt_ld = tt_nx, tn_ld = tn_nx;
     const bool obs = !isnan(y);                          // :135 (uniform over the CTA)
@@ -445,10 +517,12 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
       if (nlz && active && !(HPH > 0.0)) atomicCAS(St.status, 0, 2);   // `keyboard` trap (:408-410)
     }
     // ---- off the critical path: next step's loads, previous step's outputs ----
-    if (k + 1 < T) {
+    if (k + 1 < k1) {
       y_nx = St.y[k + 1];
-      tt_nx = St.ttau[(k + 1) * M + n];
-      tn_nx = St.tnu[(k + 1) * M + n];
+      if (ld_sites) {
+        tt_nx = St.ttau[(k + 1) * M + n];
+        tn_nx = St.tnu[(k + 1) * M + n];
+      }
     }
     if (pend) flush(false);
     // predicted moments of step k (:129-132), kept apart from the posterior of step k-1
@@ -514,7 +588,7 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
     pend = true; pend_obs = obs; pend_mom = do_mom; pk = k;
     p_tt = tt; p_tn = tn; p_Z = Zm;
   }
-  if (pend) flush(true);
+  if (pend) flush(pk == T - 1);
 }
 
 }  // namespace nsagp

@@ -4,9 +4,11 @@
 #include "../../include/nsagp.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -19,6 +21,7 @@
 #include "ekf.cuh"
 #include "ekfscan.cuh"
 #include "mcrec.cuh"
+#include "comm.cuh"
 
 using namespace nsagp;
 
@@ -27,7 +30,9 @@ namespace {
 thread_local std::string g_err;
 thread_local cudaStream_t g_stream = nullptr;
 thread_local bool g_own_stream = false;
-long long g_launches = 0;
+thread_local bool g_stream_set = false;      // a caller's stream was given (nullptr = the legacy default stream is a valid choice)
+thread_local int g_device = -1;              // device the thread-local stream and memory cache belong to
+std::atomic<long long> g_launches{0};        // incremented from several host threads (emulated ranks)
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -50,7 +55,8 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 int ensure_stream() {
-  if (g_stream == nullptr) {
+  if (g_device < 0) CU(cudaGetDevice(&g_device));
+  if (!g_stream_set && g_stream == nullptr) {
     CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_own_stream = true;
   }
@@ -197,6 +203,10 @@ struct nsagp_plan {
   std::vector<cudaEvent_t> phase_ev;
   double timings[5] = {0, 0, 0, 0, 0};
   int adf_form = 0;             // 0: one CTA per signal (latency), 1: one warp per signal (many signals)
+  int adf_chunks = 0;           // > 1: first filter pass parallel in time, burn-in overlap (opt-in, approximate; adfcta.cuh AdfPar)
+  long long adf_burn = 0;
+  double* d_bstate = nullptr;   // [B][adf_chunks][n] state at the end of each chunk's burn-in
+  unsigned long long* d_adfdiag = nullptr;   // [2] bit patterns: max |mismatch|, max |mean| at the chunk boundaries
   bool ran = false;
 };
 
@@ -251,21 +261,27 @@ int nsagp_device_count(void) {
 }
 
 int nsagp_set_device(int device) {
+  if (g_device >= 0 && g_device != device) {
+    // the thread's stream and cached blocks live on the previous device: neither may be used on the new one
+    if (g_own_stream && g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); }
+    g_stream = nullptr; g_own_stream = false; g_stream_set = false;
+    g_cache.clear();
+  }
   CU(cudaSetDevice(device));
+  g_device = device;
   return NSAGP_OK;
 }
 
 int nsagp_set_stream(void* s) {
-  if (g_own_stream && g_stream) cudaStreamDestroy(g_stream);
+  if (g_own_stream && g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); }
   g_own_stream = false;
-  g_stream = static_cast<cudaStream_t>(s);
+  g_stream = static_cast<cudaStream_t>(s);      // 0 = the legacy default stream (what torch.cuda.current_stream() is by default)
+  g_stream_set = true;
   return NSAGP_OK;
 }
 
 int64_t nsagp_launch_count(int reset) {
-  const long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 // ------------------------------------------------------------------ mom batch
@@ -628,6 +644,33 @@ int nsagp_plan_set_adf_form(nsagp_plan* pl, int form) {
   return NSAGP_OK;
 }
 
+int nsagp_plan_set_adf_parallel(nsagp_plan* pl, int32_t chunks, int64_t burnin) {
+  if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
+  if (chunks < 0 || burnin < 0) return fail(NSAGP_ERR_INVALID, "chunks and burnin must be >= 0");
+  if (chunks > 1 && burnin < 1) return fail(NSAGP_ERR_INVALID, "a parallel first pass needs a burn-in of at least one step");
+  if (chunks > 4096) return fail(NSAGP_ERR_INVALID, "at most 4096 chunks");
+  pl->adf_chunks = chunks > 1 ? chunks : 0;
+  pl->adf_burn = burnin;
+  if (pl->adf_chunks && !pl->d_adfdiag) {
+    int rc = pl->arena.alloc(&pl->d_adfdiag, 2);
+    if (rc) return rc;
+    CU(cudaMemset(pl->d_adfdiag, 0, 16));
+  }
+  if (pl->adf_chunks) {       // (re)size the burn-in state record
+    int rc = pl->arena.alloc(&pl->d_bstate, (size_t)pl->B * pl->adf_chunks * pl->n);
+    if (rc) return rc;
+  }
+  return NSAGP_OK;
+}
+
+int nsagp_plan_adf_mismatch(nsagp_plan* pl, double* out2) {
+  if (!pl || !out2) return fail(NSAGP_ERR_INVALID, "null argument");
+  out2[0] = out2[1] = 0.0;
+  if (!pl->d_adfdiag) return NSAGP_OK;
+  CU(cudaMemcpy(out2, pl->d_adfdiag, 16, cudaMemcpyDeviceToHost));     // bit patterns of non-negative doubles
+  return NSAGP_OK;
+}
+
 int nsagp_plan_destroy(nsagp_plan* pl) {
   if (!pl) return NSAGP_OK;
   pl->arena.release();
@@ -754,7 +797,26 @@ AdfGeom adf_geom(const nsagp_plan* pl, bool want_tables, bool fullstate) {
 #define DISPATCH_SINGLE(SV, ...)                                          \
   if (SV) { constexpr bool SINGLE_ = true; __VA_ARGS__; } else { constexpr bool SINGLE_ = false; __VA_ARGS__; }
 
-int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double damp, int running) {
+// Chunk geometry of the parallel-in-time first pass over the window [w0, w1).
+AdfPar adf_par(const nsagp_plan* pl, long long w0, long long w1, int& nch) {
+  AdfPar par;
+  nch = (int)std::max<long long>(1, std::min<long long>(pl->adf_chunks, (w1 - w0 + 63) / 64));    // >= 64 steps per chunk
+  par.w0 = w0; par.w1 = w1; par.chunk_len = (w1 - w0 + nch - 1) / nch; par.burn = pl->adf_burn; par.bstate = pl->d_bstate;
+  nch = (int)((w1 - w0 + par.chunk_len - 1) / par.chunk_len);
+  return par;
+}
+
+int adf_mismatch(nsagp_plan* pl, const AdfPar& par, int nch) {
+  if (nch < 2) return NSAGP_OK;
+  adf_mismatch_kernel<<<pl->B, 128, 0, g_stream>>>(pl->d_probs, pl->d_states, par, nch, pl->d_adfdiag);
+  LAUNCH_CHECK();
+  return NSAGP_OK;
+}
+
+int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double damp, int running, bool parallel = false) {
+  AdfPar par{0, 0, 0, 0, nullptr};
+  int nch = 1;
+  if (parallel && pl->adf_chunks > 1 && pl->adf_form == 0 && mom_all && !running) par = adf_par(pl, k0, k1, nch);
   if (pl->adf_form == 1) {
     const size_t sm = 64 * sizeof(double) + lik_smem_bytes(pl);
     DISPATCH_DP(pl->DP, DISPATCH_BM(pl->BM, {
@@ -770,15 +832,15 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
     if (g.tab_smem) {
       auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_, true>;
       if (g.smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-      kern<<<pl->B, g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
+      kern<<<dim3(pl->B, nch), g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running, par);
     } else {
       auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_, false>;
       if (g.smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-      kern<<<pl->B, g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running);
+      kern<<<dim3(pl->B, nch), g.threads, g.smem, g_stream>>>(pl->d_probs, pl->d_states, pl->T, k0, k1, mom_all, damp, running, par);
     }
   })));
   LAUNCH_CHECK();
-  return NSAGP_OK;
+  return adf_mismatch(pl, par, nch);
 }
 
 // Geometry of the three-phase scan (scan.cuh): CH chunks of kScanSteps steps per CTA tile, limited
@@ -831,7 +893,7 @@ int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
 
 // phases 2 and 3; prev_host: nprev aggregates [nprev][M][W] of the shards processed before this one
 template <class Elem>
-int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev) {
+int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev, bool prev_on_device = false) {
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
   const dim3 block(pl->M, a.CH);          // one thread per (latent, chunk): M <= 32 lanes in x, no warp-level operations in the scans
   const dim3 grid((unsigned)ntiles, pl->B);
@@ -840,7 +902,8 @@ int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev) 
   if (nprev > 0) {
     if (pl->B != 1 || nprev > kMaxPrevShards) return fail(NSAGP_ERR_INVALID, "time-chunked scans need B = 1 and at most 16 shards");
     const size_t w = (size_t)pl->M * Elem::kMapDoubles;
-    CU(cudaMemcpyAsync(pl->d_tile - (size_t)nprev * w, prev_host, (size_t)nprev * w * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    if (!prev_on_device)
+      CU(cudaMemcpyAsync(pl->d_tile - (size_t)nprev * w, prev_host, (size_t)nprev * w * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   }
   a.nprev = nprev;
   {
@@ -893,7 +956,7 @@ int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
   if (pl->mode != NSAGP_MODE_PREDICT) {
     // nlZ mode: a single ADF sweep (ihgp_ep_modulator_nmf.m:533-624)
     if ((rc = tm.begin(1))) return rc;
-    if ((rc = ihgp_adf(pl, 0, T, 1, pl->damping[0], pl->mode == NSAGP_MODE_NLZ_RUNNING))) return rc;
+    if ((rc = ihgp_adf(pl, 0, T, 1, pl->damping[0], pl->mode == NSAGP_MODE_NLZ_RUNNING, true))) return rc;
     if ((rc = tm.end())) return rc;
     return launch_sum(pl, pl->ep_itts, 1);
   }
@@ -901,7 +964,7 @@ int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {
   for (int itt = 1; itt <= pl->ep_itts; ++itt) {
     if ((rc = reset_diag(pl))) return rc;
     if (itt == 1) {
-      if ((rc = tm.begin(1)) || (rc = ihgp_adf(pl, 0, T, 1, damp, 0)) || (rc = tm.end())) return rc;
+      if ((rc = tm.begin(1)) || (rc = ihgp_adf(pl, 0, T, 1, damp, 0, true)) || (rc = tm.end())) return rc;
       if ((rc = launch_sum(pl, 0, 1))) return rc;
     } else {
       if ((rc = tm.begin(2))) return rc;
@@ -955,6 +1018,7 @@ int plan_reset(nsagp_plan* pl) {
   }
   CU(cudaMemsetAsync(pl->d_nlZ, 0, (size_t)pl->B * (pl->ep_itts + 1) * 8, g_stream));
   CU(cudaMemsetAsync(pl->d_diag, 0, (size_t)pl->B * pl->ep_itts * 16, g_stream));
+  if (pl->d_adfdiag) CU(cudaMemsetAsync(pl->d_adfdiag, 0, 16, g_stream));
   return NSAGP_OK;
 }
 
@@ -963,6 +1027,7 @@ int plan_reset(nsagp_plan* pl) {
 #include "api_full.inc"
 #include "api_ekf.inc"
 #include "api_chunk.inc"
+#include "api_comm.inc"
 #include "api_tables.inc"
 #include "api_mc.inc"
 

@@ -156,6 +156,18 @@ class Plan:
         _lib.check(_lib.lib().nsagp_plan_set_adf_form(self._h, int(form)))
         return self
 
+    def set_adf_parallel(self, chunks, burnin):
+        """Opt-in, approximate: first filter pass as `chunks` parallel time chunks with `burnin` steps of burn-in
+        overlap each (include/nsagp.h).  chunks <= 1 restores the exact sequential pass."""
+        _lib.check(_lib.lib().nsagp_plan_set_adf_parallel(self._h, int(chunks), int(burnin)))
+        return self
+
+    def adf_mismatch(self):
+        """(max |boundary mismatch of the means|, max |mean| there) of the last run with a parallel first pass."""
+        out = np.zeros(2)
+        _lib.check(_lib.lib().nsagp_plan_adf_mismatch(self._h, _lib.dptr(out)))
+        return float(out[0]), float(out[1])
+
     def run(self):
         _lib.check(_lib.lib().nsagp_plan_run(self._h))
         return self

@@ -68,3 +68,150 @@ def test_chunked_matches_single_plan(nsagp, gpu_lib, world, T, gaps, kind):
         assert got["n_negcav"] == ref["n_negcav"]
     for p in plans + [single]:
         p.close()
+
+
+# ----------------------------------------------------------------------------- device-side exchange (csrc/comm.cuh)
+def _run_threads(nsagp, plans, par=None):
+    """Emulated ranks: one thread per plan, mailboxes wired by device address, one C call per rank."""
+    world = len(plans)
+    cms = nsagp.chunked.DeviceComm.connect_threads(plans)
+    ranges, errors = [None] * world, []
+
+    def work(r):
+        try:
+            if par:
+                plans[r].set_adf_parallel(*par)
+            ranges[r] = nsagp.chunked.run_chunked_device(plans[r], cms[r])
+        except Exception as e:                                   # pragma: no cover - surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    return ranges[0], cms
+
+
+def _assemble(plans, ranges, names):
+    """Every rank's own range of the time-indexed outputs (what gather_outputs does across processes)."""
+    parts = [p.fetch(0, names) for p in plans]
+    out = {}
+    T = plans[0].T
+    for nm in names:
+        a0 = parts[0][nm]
+        if isinstance(a0, np.ndarray) and a0.ndim == 2 and a0.shape[1] == T and not (nm == "Varft" and plans[0].kind == 0):
+            full = np.empty_like(a0)
+            for r, (lo, hi) in enumerate(ranges):
+                full[:, lo:hi] = parts[r][nm][:, lo:hi]
+            out[nm] = full
+        else:
+            out[nm] = [p[nm] for p in parts]
+    return out
+
+
+@pytest.mark.parametrize("kind", ["ihgp", "full"])
+@pytest.mark.parametrize("world,T,gaps", [(1, 900, False), (2, 1500, False), (3, 2000, True), (4, 1111, False)])
+def test_device_exchange_matches_single_plan(nsagp, gpu_lib, world, T, gaps, kind):
+    """Exact mode: replicated first pass, every later pass sharded, carries exchanged through the mailboxes."""
+    itts = 4
+    damping = np.linspace(0.3, 0.1, itts)
+    pb = make_problem(nsagp, 6, 3, T, "exp", "matern52", seed=5 + world, kind="precalc", p=9, shift=1.0, gaps=gaps)
+    names = ("Eft", "Varft", "lb", "ub", "ttau", "tnu", "R", "MS", "MF", "nlZ", "maxDiffM")
+    single = _plans(nsagp, pb, itts, damping, 1, kind)[0]
+    single.run()
+    ref = single.fetch(0, names)
+    plans = _plans(nsagp, pb, itts, damping, world, kind)
+    for rep in range(2):                                          # a second run reuses the mailboxes (sequence numbers go on)
+        ranges, cms = _run_threads(nsagp, plans) if rep == 0 else (ranges, cms)
+        if rep == 1:
+            errors = []
+            def again(r):
+                try:
+                    nsagp.chunked.run_chunked_device(plans[r], cms[r])
+                except Exception as e:                            # pragma: no cover
+                    errors.append(e)
+            th = [threading.Thread(target=again, args=(r,)) for r in range(world)]
+            [t.start() for t in th]; [t.join() for t in th]
+            assert not errors, errors
+        got = _assemble(plans, ranges, names)
+        for k in ("Eft", "lb", "ub", "ttau", "tnu", "R", "MS", "MF") + (("Varft",) if kind == "full" else ()):
+            assert rel_err(got[k], ref[k]) < 1e-6, (k, rep)
+        for r in range(world):                                    # scalars: identical on every rank
+            assert rel_err(got["nlZ"][r], ref["nlZ"]) < 1e-8
+            assert rel_err(got["maxDiffM"][r], ref["maxDiffM"]) < 1e-6
+            if kind == "ihgp":
+                assert rel_err(got["Varft"][r], ref["Varft"]) < 1e-6
+    for c in cms:
+        c.close()
+    for p in plans + [single]:
+        p.close()
+
+
+def _short_memory_problem(nsagp, D, N, T, seed, kind):
+    """Model whose slowest latent forgets within a few hundred steps, so a burn-in of ~2000 steps is exact to rounding."""
+    rng = np.random.default_rng(seed)
+    hyp = nsagp.synth.demo_hypers(D, N, rng)
+    hyp.len_fast = 20 + 30 * rng.random(D)
+    hyp.len_slow = np.linspace(25.0, 60.0, N)
+    y, _, _ = nsagp.synth.sample_signal(hyp, "exp", "matern52", T, rng, link_shift=1.0, sqrt_model=True)
+    wn, xn = nsagp.utp_ws(9, N)
+    return dict(hyp=hyp, y=y, D=D, N=N, T=T, kernel1="exp", kernel2="matern52",
+                mom_gpu=nsagp.likModulatorPreCalcwn(nsagp.Softplus(1.0), wn, xn))
+
+
+@pytest.mark.parametrize("kind", ["ihgp", "full"])
+def test_parallel_adf_burnin_single_gpu(nsagp, gpu_lib, kind):
+    """Opt-in parallel-in-time first pass: 12 chunks with burn-in overlap on one GPU against the exact sequential
+    pass.  With a burn-in much longer than the model's memory the two agree to rounding; with a short burn-in they do
+    not, and the reported boundary mismatch says so."""
+    T, itts = 30000, 2
+    damping = np.linspace(0.3, 0.2, itts)
+    pb = _short_memory_problem(nsagp, 6, 3, T, 11, kind)
+    names = ("Eft", "ttau", "tnu", "MF", "MS", "nlZ", "lZ")
+    exact, par, short = _plans(nsagp, pb, itts, damping, 3, kind)
+    exact.run()
+    ref = exact.fetch(0, names)
+    par.set_adf_parallel(12, 2500).run()
+    got = par.fetch(0, names)
+    mis, scale = par.adf_mismatch()
+    assert 0 < scale and mis <= 1e-9 * scale, (mis, scale)
+    assert rel_err(got["nlZ"], ref["nlZ"]) < 1e-8
+    for k in ("Eft", "ttau", "tnu", "MF", "MS"):
+        assert rel_err(got[k], ref[k]) < 1e-6, k
+    short.set_adf_parallel(12, 8).run()
+    mis_s, scale_s = short.adf_mismatch()
+    assert mis_s > 1e-6 * scale_s                                  # the error estimate is not vacuous
+    assert exact.adf_mismatch() == (0.0, 0.0)
+    # switching it off restores the exact pass bit for bit
+    short.set_adf_parallel(0, 0).run()
+    back = short.fetch(0, ("MF", "ttau"))
+    assert np.array_equal(back["MF"], ref["MF"]) and np.array_equal(back["ttau"], ref["ttau"])
+    for p in (exact, par, short):
+        p.close()
+
+
+@pytest.mark.parametrize("kind", ["ihgp", "full"])
+def test_parallel_adf_sharded_over_ranks(nsagp, gpu_lib, kind):
+    """The first pass sharded over 3 emulated ranks (each rank: its own range in 4 burn-in chunks), everything else
+    through the device-side exchange: against the exact single-plan run."""
+    T, itts, world = 24000, 3, 3
+    damping = np.linspace(0.3, 0.2, itts)
+    pb = _short_memory_problem(nsagp, 6, 3, T, 12, kind)
+    names = ("Eft", "ttau", "tnu", "MF", "MS", "nlZ")
+    single = _plans(nsagp, pb, itts, damping, 1, kind)[0]
+    single.run()
+    ref = single.fetch(0, names)
+    plans = _plans(nsagp, pb, itts, damping, world, kind)
+    ranges, cms = _run_threads(nsagp, plans, par=(4, 2500))
+    got = _assemble(plans, ranges, names)
+    for k in ("Eft", "ttau", "tnu", "MF", "MS"):
+        assert rel_err(got[k], ref[k]) < 1e-6, k
+    for r in range(world):
+        assert rel_err(got["nlZ"][r], ref["nlZ"]) < 1e-8
+        mis, scale = plans[r].adf_mismatch()
+        assert mis <= 1e-9 * max(scale, 1e-300)
+    assert plans[1].adf_mismatch()[1] > 0                          # rank 1 compared its first chunk with rank 0's last step
+    for c in cms:
+        c.close()
+    for p in plans + [single]:
+        p.close()

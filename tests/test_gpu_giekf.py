@@ -137,3 +137,24 @@ def _dense_model(pb, k1, k2, D, N):
     F, L, H, Pinf, _ = ssmodel.balance_ss(F, L, H, Pinf)
     A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)
     return A, Q, H, Pinf, math.exp(float(np.ravel(lik_param)[0])), Wnmf
+
+
+@pytest.mark.parametrize("g_iter", [1, 3])
+def test_giekf_c4_shape_n73_matches_oracle(nsagp, gpu_lib, giekf_form, g_iter):
+    """BASELINE config C4's own shape (D = 32 exp subbands, N = 3 matern52 modulators: dense n = 73) with
+    missing-data gaps, against the oracle (not against another GPU kernel), both smoother forms."""
+    from oracle import giekf
+    D, N, T, k1, k2 = 32, 3, 300, "exp", "matern52"
+    pb = make_problem(nsagp, D, N, T, k1, k2, seed=404, kind="power", p=9, gaps=True, w_lik=1e-2, speech=True)
+    w = pb["hyp"].pack_log()
+    Eo, Vo, _, lbo, ubo, oo = giekf.gf_giekf_modulator_nmf(w, pb["t"], pb["y"], pb["ss_ref"], None, pb["t"], k1, k2, 1, D, N,
+                                                           g_iter, 1, want_cov=True)
+    assert oo["MS"].shape[0] == 73 and np.isnan(pb["y"]).sum() > 10
+    for form, cl, sc, tol in ((1, 0, 0, TOL), (2, 0, 0, 1e-6), (2, 23, 5, 1e-6)):
+        giekf_form(form, cl, sc)
+        Eg, Vg, _, lbg, ubg, og = nsagp.gf_giekf_modulator_nmf(w, pb["t"], pb["y"], pb["ss_gpu"], None, pb["t"], k1, k2, 1, D, N,
+                                                               g_iter, 1, debug_cov=True)
+        assert rel_err(Eg, Eo) < tol and rel_err(Vg, Vo) < tol, form
+        assert rel_err(lbg, lbo) < tol and rel_err(ubg, ubo) < tol
+        assert rel_err(og["MF"], oo["MF"]) < tol and rel_err(og["MS"], oo["MS"]) < tol
+        assert rel_err(og["PF"], oo["PF"]) < tol and rel_err(og["PS"], oo["PS"]) < tol
