@@ -30,6 +30,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")      # before torch initialises CUDA (see _lib.py)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -402,7 +404,8 @@ def run_gpu(args):
         t_ex = time.perf_counter()
         for name, fn in (("c3_one_signal_500k", lambda: bw.one_signal_chunked(ctx, "full", 500000, 20, 7, label="C3")),
                          ("ihgp_one_signal_10M", lambda: bw.one_signal_chunked(ctx, "ihgp", args.long_T, 20, 9, reps=1, warm=1,
-                                                                               exact=(world == 1), label="north_star 10M")),
+                                                                               exact=(world == 1), burnin=100000,
+                                                                               label="north_star 10M")),
                          ("c5_batch_256_clips", lambda: bw.c5_batch(ctx)),
                          ("c4_giekf", lambda: bw.c4_giekf(ctx))):
             try:

@@ -11,6 +11,12 @@ import sys
 
 import numpy as np
 
+# Kernels must be loaded when the library is: a rank that spins in comm_exchange_kernel for a peer's record must never
+# keep that peer (another thread of the same process in the emulated-rank tests, csrc/comm.cuh) from loading a kernel
+# lazily -- a lazy load synchronises with the running spin kernel and the two wait for each other.  Read by the driver
+# at CUDA initialisation, so it only helps if set before that; bench.py and tests/conftest.py set it first thing too.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # NSAGP_LIB: load another build of the same sources (e.g. an instrumented debug build)

@@ -2,6 +2,8 @@ import importlib
 import os
 import sys
 
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")      # before CUDA initialises (see _lib.py)
+
 import numpy as np
 import pytest
 
