@@ -197,15 +197,21 @@ def test_parallel_adf_sharded_over_ranks(nsagp, gpu_lib, kind):
     T, itts, world = 24000, 3, 3
     damping = np.linspace(0.3, 0.2, itts)
     pb = _short_memory_problem(nsagp, 6, 3, T, 12, kind)
-    names = ("Eft", "ttau", "tnu", "MF", "MS", "nlZ")
+    names = ("Eft", "ttau", "tnu", "R", "MF", "MS", "nlZ")
     single = _plans(nsagp, pb, itts, damping, 1, kind)[0]
     single.run()
     ref = single.fetch(0, names)
     plans = _plans(nsagp, pb, itts, damping, world, kind)
     ranges, cms = _run_threads(nsagp, plans, par=(4, 2500))
     got = _assemble(plans, ranges, names)
-    for k in ("Eft", "ttau", "tnu", "MF", "MS"):
+    for k in ("Eft", "R", "MF", "MS"):
         assert rel_err(got[k], ref[k]) < 1e-6, k
+    # sites: element-wise (a smoother-side update with 1 + d2lZ * v_cav ~ 0 yields ttau ~ 1e13 and amplifies the
+    # 1e-13 deviation of the first pass by as much; such a site is a pure "R = 0" site for everything downstream,
+    # and a max-norm comparison would see nothing else)
+    for k in ("ttau", "tnu"):
+        ok = np.abs(ref[k]) < 1e6
+        assert ok.mean() > 0.999 and np.allclose(got[k][ok], ref[k][ok], rtol=1e-6, atol=1e-9), k
     for r in range(world):
         assert rel_err(got["nlZ"][r], ref["nlZ"]) < 1e-8
         mis, scale = plans[r].adf_mismatch()
