@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -22,6 +23,7 @@
 #include "ekfscan.cuh"
 #include "mcrec.cuh"
 #include "comm.cuh"
+#include "siteupd.cuh"
 
 using namespace nsagp;
 
@@ -191,6 +193,9 @@ struct nsagp_plan {
   double* d_tile = nullptr;     // scan: one map per (CTA tile, block)
   double* d_start = nullptr;    // scan: state entering each CTA tile
   double* d_total = nullptr;    // scan: this plan's single aggregate (time-chunked runs)
+  double* d_seg = nullptr;      // two-level carry: one map per (segment of tiles, block)
+  double* d_segstart = nullptr; // two-level carry: state entering each segment
+  long long nseg_max = 0;
   long long t0 = 0, t1 = -1;    // shard of the frozen-site passes this plan executes (time-chunked runs)
   double* d_nlZ = nullptr;      // [B][ep_itts + 1]  (last slot: edata)
   double* d_diag = nullptr;     // [B][ep_itts][2]
@@ -480,6 +485,34 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
     }
     std::vector<double> W, wn, xn;
     build_lik_arrays(l, D, N, DP, W, wn, xn);
+    {
+      // distinct sigma-point coordinates per modulator (common.cuh: DevProblem::ndist)
+      std::vector<double> xd((size_t)kNP * kMaxDist, 0.0);
+      std::vector<unsigned char> xi((size_t)kNP * l.S, 0);
+      int nd = 0;
+      bool ok = true;
+      for (int j = 0; j < N && ok; ++j) {
+        int cnt = 0;
+        for (int s_ = 0; s_ < l.S && ok; ++s_) {
+          const double v = xn[(size_t)j * l.S + s_];
+          int q = 0;
+          while (q < cnt && std::memcmp(&xd[(size_t)j * kMaxDist + q], &v, 8) != 0) ++q;
+          if (q == cnt) { if (cnt == kMaxDist) { ok = false; break; } xd[(size_t)j * kMaxDist + cnt++] = v; }
+          xi[(size_t)j * l.S + s_] = (unsigned char)q;
+        }
+        nd = std::max(nd, cnt);
+      }
+      P.ndist = 0;
+      static const bool no_tab = std::getenv("NSAGP_NO_LINK_TABLE") != nullptr;      // (A/B measurements)
+      if (ok && !no_tab && nd > 0 && nd * 3 <= l.S) {            // worth it only if it saves most link evaluations
+        std::vector<double> xdp((size_t)kNP * nd, 0.0);
+        for (int j = 0; j < kNP; ++j)
+          for (int q = 0; q < nd; ++q) xdp[(size_t)j * nd + q] = xd[(size_t)j * kMaxDist + q];
+        double* dxd; unsigned char* dxi;
+        if ((rc = pl->arena.upload(&dxd, xdp)) || (rc = pl->arena.upload(&dxi, xi))) return cleanup(rc);
+        P.ndist = nd; P.xdist = dxd; P.xidx = dxi;
+      }
+    }
     double *dA, *dQ, *dPi, *dh, *dhA, *dW, *dwn, *dxn;
     if ((rc = pl->arena.upload(&dA, A)) || (rc = pl->arena.upload(&dQ, Q)) || (rc = pl->arena.upload(&dPi, Pi)) ||
         (rc = pl->arena.upload(&dh, h)) || (rc = pl->arena.upload(&dhA, hA)) || (rc = pl->arena.upload(&dW, W)) ||
@@ -610,6 +643,8 @@ int nsagp_plan_create(nsagp_plan** out_plan, int32_t kind, int32_t B, const nsag
       (rc = pl->arena.alloc(&pl->d_tile, ((size_t)B * ntiles_max + kMaxPrevShards) * M * map_d)) ||
       (rc = pl->arena.alloc(&pl->d_start, ((size_t)B * ntiles_max + kMaxPrevShards) * M * state_d)) ||
       (rc = pl->arena.alloc(&pl->d_total, (size_t)M * map_d)) ||
+      (rc = pl->arena.alloc(&pl->d_seg, (size_t)B * (pl->nseg_max = (long long)std::ceil(std::sqrt((double)(ntiles_max + kMaxPrevShards))) + 2) * M * map_d)) ||
+      (rc = pl->arena.alloc(&pl->d_segstart, (size_t)B * pl->nseg_max * M * state_d)) ||
       (rc = pl->arena.alloc(&pl->d_nlZ, (size_t)B * (pl->ep_itts + 1))) ||
       (rc = pl->arena.alloc(&pl->d_diag, (size_t)B * pl->ep_itts * 2)))
     return cleanup(rc);
@@ -748,6 +783,13 @@ struct PhaseTimer {
 
 size_t lik_smem_bytes(const nsagp_plan* pl) {
   return ((size_t)pl->DP * kNP + (size_t)pl->S * (1 + kNP)) * sizeof(double);
+}
+
+// all problems of a plan share S; the link table is used only if every problem has one of the same size
+size_t site_tab_bytes(const nsagp_plan* pl, int TPB) {
+  int nd = pl->h_probs.empty() ? 0 : pl->h_probs[0].ndist;
+  for (const DevProblem& P : pl->h_probs) nd = std::max(nd, P.ndist);
+  return (size_t)site_tab_doubles(nd, pl->S, TPB) * sizeof(double);
 }
 
 int launch_sum(nsagp_plan* pl, int slot, int neg, long long k0 = 0, long long k1 = -1) {
@@ -908,11 +950,34 @@ int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev, 
   a.nprev = nprev;
   {
     const size_t per_tile = (size_t)pl->M * Elem::kMapDoubles * sizeof(double);
-    int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)(ntiles + nprev), (64 * 1024) / per_tile));
-    const size_t sm2 = per_tile * batch;
-    if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(scan_carry_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-    scan_carry_kernel<Elem><<<pl->B, kCarryThreads, sm2, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_tile, pl->d_start, batch);
-    LAUNCH_CHECK();
+    const long long nlist = ntiles + nprev;                   // maps the walk passes through (per problem)
+    auto carry = [&](const double* maps, double* starts, long long nmaps, long long count) -> int {
+      int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, (64 * 1024) / per_tile));
+      const size_t sm2 = per_tile * batch;
+      if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(scan_carry_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      scan_carry_kernel<Elem><<<pl->B, kCarryThreads, sm2, g_stream>>>(pl->d_probs, pl->d_states, a, maps, starts, batch, nmaps);
+      LAUNCH_CHECK();
+      return NSAGP_OK;
+    };
+    if (nlist <= 96) {
+      int rc = carry(pl->d_tile, pl->d_start, 0, nlist);
+      if (rc) return rc;
+    } else {
+      // two-level carry (scan.cuh): segments of ~sqrt(nlist) tiles
+      int seg_len = (int)std::ceil(std::sqrt((double)nlist));
+      const long long nseg = (nlist + seg_len - 1) / seg_len;
+      if (nseg > pl->nseg_max) return fail(NSAGP_ERR_INVALID, "internal: segment scratch too small");
+      const double* maps = pl->d_tile - (size_t)nprev * pl->M * Elem::kMapDoubles;
+      double* starts = pl->d_start - (size_t)nprev * pl->M * Elem::kStateDoubles;
+      const int gy = std::max(1, 128 / pl->M);
+      const dim3 sblock(pl->M, gy), sgrid((unsigned)((nseg + gy - 1) / gy), pl->B);
+      carry_seg_reduce_kernel<Elem><<<sgrid, sblock, 0, g_stream>>>(pl->d_probs, maps, pl->d_seg, nlist, seg_len);
+      LAUNCH_CHECK();
+      int rc = carry(pl->d_seg, pl->d_segstart, nseg, nseg);
+      if (rc) return rc;
+      carry_seg_apply_kernel<Elem><<<sgrid, sblock, 0, g_stream>>>(pl->d_probs, maps, pl->d_segstart, starts, nlist, seg_len);
+      LAUNCH_CHECK();
+    }
   }
   scan_apply_kernel<Elem><<<grid, block, sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start);
   LAUNCH_CHECK();
@@ -935,19 +1000,40 @@ int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int
   return rc;
 }
 
-int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ, long long k0 = 0, long long k1 = -1) {
-  if (k1 < 0) k1 = pl->T - 1;
-  if (k1 <= k0) return NSAGP_OK;
-  constexpr int TPB = 64;
-  const size_t sm = (size_t)4 * pl->M * TPB * sizeof(double) + lik_smem_bytes(pl);
-  const dim3 grid((unsigned)((k1 - k0 + TPB - 1) / TPB), pl->B);
-  DISPATCH_DP(pl->DP, {
-    auto kern = site_update_kernel<DP_, TPB, false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, k0, k1, pl->alpha, damp, write_lZ, 0);
+// Smoother-side site update over steps [k0, k1): four lanes per step (siteupd.cuh); NSAGP_SITE_FORM=1 selects the
+// first-generation one-thread-per-step kernel (kept as an independent cross-check).
+template <bool FULL>
+int site_update_launch(nsagp_plan* pl, double damp, int write_lZ, int clamp_R, long long k0, long long k1) {
+  static const bool old_form = std::getenv("NSAGP_SITE_FORM") && std::atoi(std::getenv("NSAGP_SITE_FORM")) == 1;
+  if (old_form) {
+    constexpr int TPB = 64;
+    const size_t sm = (size_t)4 * pl->M * TPB * sizeof(double) + lik_smem_bytes(pl) + site_tab_bytes(pl, TPB);
+    const dim3 grid((unsigned)((k1 - k0 + TPB - 1) / TPB), pl->B);
+    DISPATCH_DP(pl->DP, {
+      auto kern = site_update_kernel<DP_, TPB, FULL>;
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      kern<<<grid, TPB, sm, g_stream>>>(pl->d_probs, pl->d_states, k0, k1, pl->alpha, damp, write_lZ, clamp_R);
+    });
+    LAUNCH_CHECK();
+    return NSAGP_OK;
+  }
+  int nd = 0;
+  for (const DevProblem& P : pl->h_probs) nd = std::max(nd, P.ndist);
+  const size_t sm = (size_t)site4_smem_doubles(pl->M, pl->S, nd, FULL) * sizeof(double);
+  const dim3 grid((unsigned)((k1 - k0 + kSiteSteps - 1) / kSiteSteps), pl->B);
+  DISPATCH_DPT((pl->D <= 16) ? 4 : 8, {
+    auto kern = site_update4_kernel<DPT_, FULL>;
+    if (sm > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<grid, kSiteThreads, sm, g_stream>>>(pl->d_probs, pl->d_states, k0, k1, pl->alpha, damp, write_lZ, clamp_R);
   });
   LAUNCH_CHECK();
   return NSAGP_OK;
+}
+
+int ihgp_site_update(nsagp_plan* pl, double damp, int write_lZ, long long k0 = 0, long long k1 = -1) {
+  if (k1 < 0) k1 = pl->T - 1;
+  if (k1 <= k0) return NSAGP_OK;
+  return site_update_launch<false>(pl, damp, write_lZ, 0, k0, k1);
 }
 
 int run_ihgp(nsagp_plan* pl, PhaseTimer& tm) {

@@ -12,6 +12,7 @@ constexpr int kWarp = 32;
 constexpr double kInvSqrt2Pi = 0.39894228040143267793994605993438;
 constexpr double kJitter = 1e-10;          // likModulatorNMFPower.m:28
 constexpr int kCthrPad = 8;                // sentinels on either side of the ttau thresholds (window look-up)
+constexpr int kMaxDist = 8;                // distinct sigma-point coordinates per modulator the link table holds
 constexpr double kLookupBig = 1e12;        // above this the nearest-neighbour search is done by brute force
 
 // Per-problem constant data resident in HBM (built once by the plan).
@@ -33,6 +34,12 @@ struct DevProblem {
   const double* W;               // [DP][NP] row-major padded (DP = 16/32, NP = 4)
   const double* wn;              // [S]
   const double* xn;              // [NP][S]
+  // Distinct abscissae per modulator: the coordinates of a fully symmetric or tensor rule take few distinct values
+  // (0, +-u, +-v for utp_ws(9, N)), so the link function is evaluated ndist times per modulator and step instead of S
+  // times (same arithmetic on the same inputs: bit-identical).  ndist = 0: not available (more than kMaxDist values).
+  int ndist;
+  const double* xdist;           // [NP][ndist]
+  const unsigned char* xidx;     // [NP][S] index into xdist
   // IHGP tables
   const double* r;               // [nr]
   const double* thr;             // [nr-1] decision thresholds of the nearest-neighbour search; kCthrPad sentinels

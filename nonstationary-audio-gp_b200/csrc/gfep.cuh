@@ -431,7 +431,15 @@ struct RtsScanElem {
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) s.P[i] = src[BM + i];
   }
-  __device__ __forceinline__ void prefetch(long long) {}
+  // (no register-pipelined inputs for this element: scan.cuh scan_walk)
+  static constexpr int kPrefetch = 1;
+  struct In {};
+  struct Tab {};
+  __device__ __forceinline__ void load(long long, In&) const {}
+  __device__ __forceinline__ void lookup(long long, const In&, Tab&) const {}
+  __device__ __forceinline__ void get(long long k, const In&, const Tab&, Map& e) { get(k, e); }
+  __device__ __forceinline__ void step(long long k, const In&, const Tab&, State& s) { step(k, s); }
+  __device__ __forceinline__ void begin_apply() {}
   __device__ __forceinline__ void get(long long k, Map& e) {
     RtsStep<BM> st;
     el.step(k, st);
@@ -665,7 +673,15 @@ struct KfScanElem {
     if (nlz) tt = fmax(tt, 0.0);
     return true;
   }
-  __device__ __forceinline__ void prefetch(long long) {}
+  // (no register-pipelined inputs for this element: scan.cuh scan_walk)
+  static constexpr int kPrefetch = 1;
+  struct In {};
+  struct Tab {};
+  __device__ __forceinline__ void load(long long, In&) const {}
+  __device__ __forceinline__ void lookup(long long, const In&, Tab&) const {}
+  __device__ __forceinline__ void get(long long k, const In&, const Tab&, Map& e) { get(k, e); }
+  __device__ __forceinline__ void step(long long k, const In&, const Tab&, State& s) { step(k, s); }
+  __device__ __forceinline__ void begin_apply() {}
   __device__ __forceinline__ void get(long long k, Map& e) {
     double tt, tn;
     sites(k, tt, tn);

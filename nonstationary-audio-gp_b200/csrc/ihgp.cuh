@@ -31,6 +31,12 @@ __device__ __forceinline__ MomParams make_mom_params(const DevProblem& P, const 
   return mp;
 }
 
+// doubles of shared memory the thread-form site update needs beyond its [4][M][TPB] staging and the likelihood
+// tables: the per-thread link table and the (byte) index map
+__host__ __device__ inline int site_tab_doubles(int ndist, int S, int TPB) {
+  return ndist > 0 ? 2 * kNP * ndist * TPB + (kNP * S + 7) / 8 : 0;
+}
+
 // ------------------------------------------------------------------ ADF pass
 // One warp per signal.  Steps k0..k1-1.  mom_all: moment matching at every step
 // (first pass) or only at k == T-1 (later passes call this for the last step).
@@ -266,6 +272,7 @@ struct FilterElem : AffineElemBase<BM> {
   using State = MeanState<BM>;
   const DevProblem& P; const DevState& St; int n, off, b;
   double A[BM * BM], hA[BM];
+  __device__ __forceinline__ void begin_apply() {}
   __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
@@ -273,10 +280,33 @@ struct FilterElem : AffineElemBase<BM> {
 #pragma unroll
     for (int i = 0; i < BM; ++i) hA[i] = P.hA[n * BM + i];
   }
+  // Inputs of step k: the sites of steps k and k-1 (the look-up uses R(:,k-1), :239); table row of the look-up.
+  static constexpr int kPrefetch = 3;
+  struct In { double tt, tn, R, ttp, Rp; };
+  struct Tab { double w[BM], HPH; };
+  __device__ __forceinline__ void load(long long k, In& in) const {
+    const int M = P.M;
+    in.tt = St.ttau[k * M + n]; in.tn = St.tnu[k * M + n]; in.R = St.R[k * M + n];
+    in.ttp = k > 0 ? St.ttau[(k - 1) * M + n] : 0.0;
+    in.Rp = k > 0 ? St.R[(k - 1) * M + n] : 0.0;
+  }
+  __device__ __forceinline__ void lookup(long long k, const In& in, Tab& tb) const {
+    const int nr = P.nr;
+    int idx = nr;
+    if (k > 0) {
+      const double ttp = fmax(in.ttp, 0.0);
+      const double Rp = (ttp == 0.0) ? INFINITY : in.Rp;
+      idx = lookup_filter_hint(P, Rp);
+    }
+    const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BM;
+#pragma unroll
+    for (int i = 0; i < BM; ++i) tb.w[i] = wrow[i];
+    tb.HPH = P.HPHtab[(size_t)n * (nr + 1) + idx];
+  }
   // commit: write back the clamp / Inf marking of the reference's filter loop (:274,:287)
-  __device__ __forceinline__ void get_impl(long long k, Map& e, bool commit) {
-    const int M = P.M, nr = P.nr;
-    const double tt = fmax(St.ttau[k * M + n], 0.0);                          // :274
+  __device__ __forceinline__ void get_impl(long long k, const In& in, const Tab& tb, Map& e, bool commit) {
+    const int M = P.M;
+    const double tt = fmax(in.tt, 0.0);                                        // :274
     if (tt == 0.0) {
 #pragma unroll
       for (int i = 0; i < BM * BM; ++i) e.F[i] = A[i];
@@ -285,32 +315,20 @@ struct FilterElem : AffineElemBase<BM> {
       if (commit) { St.ttau[k * M + n] = 0.0; St.R[k * M + n] = INFINITY; }
       return;
     }
-    int idx = nr;
-    if (k > 0) {
-      const double ttp = fmax(St.ttau[(k - 1) * M + n], 0.0);
-      const double Rp = (ttp == 0.0) ? INFINITY : St.R[(k - 1) * M + n];
-      idx = lookup_filter_hint(P, Rp);
-    }
-    const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BM;
-    const double HPH = P.HPHtab[(size_t)n * (nr + 1) + idx];
-    const double g = 1.0 / (HPH + St.R[k * M + n]);
-    const double ys = St.tnu[k * M + n] / tt;
+    const double g = 1.0 / (tb.HPH + in.R);
+    const double ys = in.tn / tt;
 #pragma unroll
     for (int i = 0; i < BM; ++i) {
-      const double Ki = wrow[i] * g;
+      const double Ki = tb.w[i] * g;
       e.c[i] = Ki * ys;
 #pragma unroll
       for (int j = 0; j < BM; ++j) e.F[i + j * BM] = fma(-Ki, hA[j], A[i + j * BM]);   // A - K (h A)
     }
   }
-  __device__ __forceinline__ void get(long long k, Map& e) { get_impl(k, e, false); }
-  __device__ __forceinline__ void prefetch(long long k) {
-    const int M = P.M;
-    prefetch_l1(St.ttau + k * M + n); prefetch_l1(St.R + k * M + n); prefetch_l1(St.tnu + k * M + n);
-  }
-  __device__ __forceinline__ void step(long long k, State& s) {
+  __device__ __forceinline__ void get(long long k, const In& in, const Tab& tb, Map& e) { get_impl(k, in, tb, e, false); }
+  __device__ __forceinline__ void step(long long k, const In& in, const Tab& tb, State& s) {
     Map e;
-    get_impl(k, e, true);
+    get_impl(k, in, tb, e, true);
     affine_apply<BM>(e, s.m);
 #pragma unroll
     for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P.n + off + i] = s.m[i];
@@ -332,6 +350,8 @@ struct SmootherElem : AffineElemBase<BM> {
   const DevProblem& P; const DevState& St; int n, off, b;
   double A[BM * BM], hv[BM];
   double mdM;
+  bool applying = false;
+  __device__ __forceinline__ void begin_apply() { applying = true; }
   __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), mdM(0.0) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
@@ -339,43 +359,51 @@ struct SmootherElem : AffineElemBase<BM> {
 #pragma unroll
     for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BM + i];
   }
-  __device__ __forceinline__ void get_impl(long long k, Map& e, bool commit) {
-    const int M = P.M, nr = P.nr;
-    const int idx = lookup_smoother_hint(P, St.R[k * M + n]);
-    const double* G = P.Gtab + ((size_t)n * nr + idx) * BM * BM;
-    double ms[BM], t[BM];
+  // Inputs of step k: R(:,k) (look-up of the smoother gain), the filtered mean, H*MS of the previous iteration.
+  static constexpr int kPrefetch = 3;
+  struct In { double R, ms[BM], Eold; };
+  struct Tab { double G[BM * BM]; int idx; };
+  __device__ __forceinline__ void load(long long k, In& in) const {
+    in.R = St.R[k * P.M + n];
 #pragma unroll
-    for (int i = 0; i < BM; ++i) ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
+    for (int i = 0; i < BM; ++i) in.ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
+    in.Eold = applying ? St.E[k * P.M + n] : 0.0;
+  }
+  __device__ __forceinline__ void lookup(long long, const In& in, Tab& tb) const {
+    tb.idx = lookup_smoother_hint(P, in.R);
+    const double* G = P.Gtab + ((size_t)n * P.nr + tb.idx) * BM * BM;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) tb.G[i] = G[i];
+  }
+  __device__ __forceinline__ void get_impl(long long k, const In& in, const Tab& tb, Map& e, bool commit) {
+    double t[BM];
 #pragma unroll
     for (int i = 0; i < BM; ++i) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < BM; ++j) acc = fma(A[i + j * BM], ms[j], acc);
+      for (int j = 0; j < BM; ++j) acc = fma(A[i + j * BM], in.ms[j], acc);
       t[i] = acc;
     }
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) e.F[i] = G[i];
+    for (int i = 0; i < BM * BM; ++i) e.F[i] = tb.G[i];
 #pragma unroll
     for (int i = 0; i < BM; ++i) {
       double acc = 0.0;
 #pragma unroll
       for (int j = 0; j < BM; ++j) acc = fma(e.F[i + j * BM], t[j], acc);
-      e.c[i] = ms[i] - acc;
+      e.c[i] = in.ms[i] - acc;
     }
     if (commit && k == 0) {
       // marginal variance of the last look-up: the reference's Varft (:492) and maxDiffP (:444)
-      const double vm = P.vmtab[(size_t)n * nr + idx];
+      const double vm = P.vmtab[(size_t)n * P.nr + tb.idx];
       atomic_max_nonneg(St.maxdiff + 1, fabs(St.vm0[n] - vm));
       St.vm0[n] = vm;
     }
   }
-  __device__ __forceinline__ void get(long long k, Map& e) { get_impl(k, e, false); }
-  __device__ __forceinline__ void prefetch(long long k) {
-    prefetch_l1(St.R + k * P.M + n); prefetch_l1(St.MS + k * P.n + off); prefetch_l1(St.E + k * P.M + n);
-  }
-  __device__ __forceinline__ void step(long long k, State& s) {
+  __device__ __forceinline__ void get(long long k, const In& in, const Tab& tb, Map& e) { get_impl(k, in, tb, e, false); }
+  __device__ __forceinline__ void step(long long k, const In& in, const Tab& tb, State& s) {
     Map e;
-    get_impl(k, e, true);
+    get_impl(k, in, tb, e, true);
     affine_apply<BM>(e, s.m);
     double ev = 0.0;
 #pragma unroll
@@ -384,7 +412,7 @@ struct SmootherElem : AffineElemBase<BM> {
       ev = fma(hv[i], s.m[i], ev);
     }
     // maxDiffM (:440): against H*MS of the previous iteration's smoother
-    mdM = fmax(mdM, fabs(St.E[k * P.M + n] - ev));
+    mdM = fmax(mdM, fabs(in.Eold - ev));
     St.E[k * P.M + n] = ev;
   }
   __device__ __forceinline__ void init(State& s, int, long long kinit) {      // m starts at the filtered mean of the last step
@@ -423,9 +451,13 @@ site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
   double* s_W = s_d2 + M * TPB;            // [DP*kNP]
   double* s_wn = s_W + DP * kNP;
   double* s_xn = s_wn + P.S;
+  double* s_tab = s_xn + kNP * P.S;        // [kNP][ndist][2][TPB] link table of each thread's step
+  unsigned char* s_xi = reinterpret_cast<unsigned char*>(s_tab + 2 * kNP * P.ndist * TPB);
   for (int i = tid; i < DP * kNP; i += TPB) s_W[i] = P.W[i];
   for (int i = tid; i < P.S; i += TPB) s_wn[i] = P.wn[i];
   for (int i = tid; i < kNP * P.S; i += TPB) s_xn[i] = P.xn[i];
+  if (P.ndist > 0)
+    for (int i = tid; i < kNP * P.S; i += TPB) s_xi[i] = P.xidx[i];
   __syncthreads();
   if (k >= k1) return;
   const double y = St.y[k];
@@ -433,7 +465,8 @@ site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
     if (!FULL && write_lZ) St.lZ[k] = 0.0; // IHGP accumulates a scalar: no term for this step
     return;
   }
-  const MomParams mp = make_mom_params(P, s_W, s_wn, s_xn);
+  MomParams mp = make_mom_params(P, s_W, s_wn, s_xn);
+  mp.nd = P.ndist; mp.xd = P.xdist; mp.xi = s_xi;
   for (int n = 0; n < M; ++n) {
     double vm;
     if (FULL) {
@@ -448,7 +481,7 @@ site_update_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
     s_mu[n * TPB + tid] = mcav;
     s_s2[n * TPB + tid] = vcav;
   }
-  const double lz = mom_thread<DP>(mp, alpha, y, s_mu + tid, s_s2 + tid, TPB, s_d1 + tid, s_d2 + tid);
+  const double lz = mom_thread<DP>(mp, alpha, y, s_mu + tid, s_s2 + tid, TPB, s_d1 + tid, s_d2 + tid, s_tab + tid);
   if (write_lZ) St.lZ[k] = lz;             // ihgp :420 only from the second iteration on
   int neg = 0;
   const double keep = 1.0 - ep_damp * alpha;

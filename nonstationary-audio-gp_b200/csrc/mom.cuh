@@ -32,6 +32,9 @@ struct MomParams {
   const double* W;               // [DP][kNP] row-major, zero padded
   const double* wn;              // [S]
   const double* xn;              // [kNP][S]
+  int nd = 0;                    // link table (thread form): distinct coordinates per modulator, 0 = none
+  const double* xd = nullptr;    // [kNP][nd]
+  const unsigned char* xi = nullptr;   // [kNP][S]
 };
 
 template <int DP>
@@ -64,6 +67,12 @@ __device__ __forceinline__ double pep_const(int kind, double sn2, double alpha) 
 // FAST: the straight-line routines of fastmath.cuh (<= 2 ulp, NaN-propagating variants) instead of
 // the library's exp / log / sqrt / division; the warp form keeps the library versions so that the
 // two sequential-pass implementations stay numerically independent of each other.
+// The per-point arithmetic after the link: x[j] = the modulators' sigma-point coordinates, l[j] = link(x[j]).
+template <int DP, bool FAST>
+__device__ __forceinline__ void mom_point_xl(MomAcc<DP>& acc, const MomParams& p, const MomG& g, int s, double y, double noise,
+                                             const double* muz, const double* s2z, int stride, const double (&x)[kNP],
+                                             const double (&l)[kNP]);
+
 template <int DP, bool FAST = false>
 __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, const MomG& g, int s,
                                           double y, double noise, const double* muz,
@@ -78,6 +87,13 @@ __device__ __forceinline__ void mom_point(MomAcc<DP>& acc, const MomParams& p, c
       x[j] = 0.0; l[j] = 0.0;
     }
   }
+  mom_point_xl<DP, FAST>(acc, p, g, s, y, noise, muz, s2z, stride, x, l);
+}
+
+template <int DP, bool FAST>
+__device__ __forceinline__ void mom_point_xl(MomAcc<DP>& acc, const MomParams& p, const MomG& g, int s, double y, double noise,
+                                             const double* muz, const double* s2z, int stride, const double (&x)[kNP],
+                                             const double (&l)[kNP]) {
   double a[DP];
   double vs = 0.0, ms = 0.0;
 #pragma unroll
@@ -147,16 +163,50 @@ __device__ __forceinline__ void mom_setup_g(MomG& g, const MomParams& p, const d
 // ---------------------------------------------------------------- thread form
 // mu/s2 hold the D+N cavity means/variances of this thread's step with the given
 // stride.  Results are written to d1/d2 with the same stride; returns lZ.
+// tab (optional, with p.nd > 0): this thread's scratch for the link table, 2 * kNP * p.nd doubles at the given stride.
 template <int DP>
 __device__ __forceinline__ double mom_thread(const MomParams& p, double alpha, double y,
                                              const double* mu, const double* s2, int stride,
-                                             double* d1, double* d2) {
+                                             double* d1, double* d2, double* tab = nullptr) {
   MomAcc<DP> acc;
   acc.clear();
   MomG g;
   mom_setup_g(g, p, mu + p.D * stride, s2 + p.D * stride, stride);
   const double noise = p.sn2 / alpha;
-  for (int s = 0; s < p.S; ++s) mom_point<DP, true>(acc, p, g, s, y, noise, mu, s2, stride);
+  if (p.nd <= 0) tab = nullptr;
+  if (tab) {
+    // Link table of this step: the coordinates of a symmetric / tensor rule take p.nd distinct values per modulator,
+    // so link() is evaluated N * nd times instead of N * S times; entry (j, q) = (x, link(x)).  The entries of point
+    // s + 1 are fetched while point s is integrated (the fetch is two dependent shared-memory loads).
+    for (int j = 0; j < p.N; ++j)
+      for (int q = 0; q < p.nd; ++q) {
+        const double x = g.mu[j] + g.sd[j] * p.xd[j * p.nd + q];
+        tab[(j * p.nd + q) * 2 * stride] = x;
+        tab[(j * p.nd + q) * 2 * stride + stride] = softplus_fast(x - p.shift);
+      }
+    double xc[kNP], lc[kNP], xq[kNP], lq[kNP];
+    auto fetch = [&](int s, double (&x)[kNP], double (&l)[kNP]) {
+#pragma unroll
+      for (int j = 0; j < kNP; ++j) {
+        if (j < p.N) {
+          const int q = (j * p.nd + p.xi[j * p.S + s]) * 2 * stride;
+          x[j] = tab[q];
+          l[j] = tab[q + stride];
+        } else {
+          x[j] = 0.0; l[j] = 0.0;
+        }
+      }
+    };
+    fetch(0, xq, lq);
+    for (int s = 0; s < p.S; ++s) {
+#pragma unroll
+      for (int j = 0; j < kNP; ++j) { xc[j] = xq[j]; lc[j] = lq[j]; }
+      if (s + 1 < p.S) fetch(s + 1, xq, lq);
+      mom_point_xl<DP, true>(acc, p, g, s, y, noise, mu, s2, stride, xc, lc);
+    }
+  } else {
+    for (int s = 0; s < p.S; ++s) mom_point<DP, true>(acc, p, g, s, y, noise, mu, s2, stride);
+  }
   const double pep = pep_const(p.kind, p.sn2, alpha);
   const double Z = pep * fmax(acc.Z, kJitter);      // fmax(NaN, jitter) = jitter, as MATLAB max
   const double zp = (1.0 / Z) * pep;

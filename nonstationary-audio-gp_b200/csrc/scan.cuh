@@ -44,6 +44,38 @@ __host__ __device__ inline long long scan_num_tiles(long long nsteps, int CH) {
   return (nsteps + per - 1) / per;
 }
 
+// Walk the steps s0..s1-1 of one chunk with the element's inputs software-pipelined through registers: the raw inputs
+// of step s + kPrefetch (sites, means: loads that do not depend on anything) and the table rows of step s + 1 (loads that
+// depend on that step's sites) are requested BEFORE step s is processed.  Without this every step of a thread waits for
+// its own HBM round trip (and a dependent L2 round trip for the table row) -- 32 of them in sequence, which is what kept
+// these passes at 7-10 % of the HBM roof (profiles/r1bl_scan_full.md: long_scoreboard 29-39 stalls per issue).
+// Elements without pipelined loads declare empty In / Tab and kPrefetch = 1.
+template <class Elem, class Body>
+__device__ __forceinline__ void scan_walk(Elem& el, const ScanArgs& a, long long s0, long long s1, Body&& body) {
+  using In = typename Elem::In;
+  using Tab = typename Elem::Tab;
+  constexpr int PF = Elem::kPrefetch;
+  In ring[PF];
+  Tab tb;
+#pragma unroll
+  for (int j = 0; j < PF; ++j)
+    if (s0 + j < s1) el.load(a.kfirst + a.dir * (s0 + j), ring[j]);
+  el.lookup(a.kfirst + a.dir * s0, ring[0], tb);
+  for (long long sb = s0; sb < s1; sb += PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const long long st = sb + j;
+      if (st < s1) {
+        const In cur = ring[j];
+        const Tab tcur = tb;
+        if (st + PF < s1) el.load(a.kfirst + a.dir * (st + PF), ring[j]);
+        if (st + 1 < s1) el.lookup(a.kfirst + a.dir * (st + 1), ring[(j + 1) % PF], tb);
+        body(a.kfirst + a.dir * st, cur, tcur);
+      }
+    }
+  }
+}
+
 template <class Elem>
 __global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
                                    ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf) {
@@ -61,16 +93,13 @@ __global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const D
     Map acc;
     if (live) {
       Elem el(P, St, n, a);
-      Map e;
       const long long s0 = chunk * kScanSteps;
       const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
-      if (s0 + 1 < a.nsteps) el.prefetch(a.kfirst + a.dir * (s0 + 1));
-      el.get(a.kfirst + a.dir * s0, acc);
-      for (long long s = s0 + 1; s < s1; ++s) {
-        if (s + 2 < a.nsteps) el.prefetch(a.kfirst + a.dir * (s + 2));
-        el.get(a.kfirst + a.dir * s, e);
-        Elem::compose(acc, e);
-      }
+      bool first = true;
+      scan_walk(el, a, s0, s1, [&](long long k, const typename Elem::In& in, const typename Elem::Tab& tb) {
+        if (first) { el.get(k, in, tb, acc); first = false; }
+        else { Map e; el.get(k, in, tb, e); Elem::compose(acc, e); }
+      });
       el.finish_reduce();
       Elem::store_map(acc, chunk_buf + (((size_t)blockIdx.y * nchunks + chunk) * M + n) * W);
       Elem::store_map(acc, sm + ((size_t)c * M + n) * W);
@@ -99,7 +128,7 @@ constexpr int kCarryThreads = 256;
 template <class Elem>
 __global__ void __launch_bounds__(kCarryThreads)
 scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, ScanArgs a,
-                  const double* __restrict__ tile_buf, double* __restrict__ tile_start, int batch) {
+                  const double* __restrict__ tile_buf, double* __restrict__ tile_start, int batch, long long nmaps) {
   using Map = typename Elem::Map;
   using State = typename Elem::State;
   constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
@@ -110,9 +139,11 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   // When a signal is time-chunked over GPUs, the aggregates of the shards that come earlier in
   // processing order sit in the nprev slots before tile_buf (single-problem plans only): the
   // walk starts from the global initial state and passes through them first.
-  const long long ntiles = scan_num_tiles(a.nsteps, a.CH) + a.nprev;
-  const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W - (size_t)a.nprev * M * W;
-  double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW - (size_t)a.nprev * M * SW;
+  // nmaps > 0: walk that many maps stored at tile_buf (the segment aggregates of the two-level carry) instead
+  const long long ntiles = nmaps > 0 ? nmaps : scan_num_tiles(a.nsteps, a.CH) + a.nprev;
+  const size_t back = nmaps > 0 ? 0 : (size_t)a.nprev;
+  const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W - back * M * W;
+  double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW - back * M * SW;
   const bool walker = tid < M;
   Elem el(P, St, walker ? tid : 0, a);
   State s;
@@ -133,6 +164,58 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
     __syncthreads();
   }
   if (walker) el.store_final(s);   // the state after the last step (used by a following tile / rank)
+}
+
+// Two-level carry for long signals: the walk above is one application per CTA tile, i.e. nsteps / (32 CH) dependent
+// steps on ONE SM (0.4 ms per pass at 10^6 steps, 20-60 % of a frozen pass).  The tiles are cut into segments of
+// seg_len; thread (block n, segment g) composes its segment's tile aggregates (carry_seg_reduce), scan_carry_kernel
+// walks the few segment aggregates, and thread (n, g) replays its segment from the state entering it, recording the
+// state entering every tile (carry_seg_apply): 3 sqrt(ntiles) dependent steps instead of ntiles.
+// tile_buf / tile_start point at the FIRST map of the list (including the nprev shard aggregates in front).
+template <class Elem>
+__global__ void carry_seg_reduce_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ tile_buf,
+                                        double* __restrict__ seg_buf, long long ntiles, int seg_len) {
+  using Map = typename Elem::Map;
+  constexpr int W = Elem::kMapDoubles;
+  const int M = probs[blockIdx.y].M, n = threadIdx.x;
+  const long long g = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long nseg = (ntiles + seg_len - 1) / seg_len;
+  if (n >= M || g >= nseg) return;
+  const long long t0 = g * seg_len;
+  const long long t1 = t0 + seg_len < ntiles ? t0 + seg_len : ntiles;
+  const double* src = tile_buf + (size_t)blockIdx.y * ntiles * M * W;
+  Map acc, e;
+  Elem::load_map(acc, src + ((size_t)t0 * M + n) * W);
+  for (long long t = t0 + 1; t < t1; ++t) {
+    Elem::load_map(e, src + ((size_t)t * M + n) * W);
+    Elem::compose(acc, e);
+  }
+  Elem::store_map(acc, seg_buf + (((size_t)blockIdx.y * nseg + g) * M + n) * W);
+}
+
+template <class Elem>
+__global__ void carry_seg_apply_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ tile_buf,
+                                       const double* __restrict__ seg_start, double* __restrict__ tile_start,
+                                       long long ntiles, int seg_len) {
+  using Map = typename Elem::Map;
+  using State = typename Elem::State;
+  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
+  const int M = probs[blockIdx.y].M, n = threadIdx.x;
+  const long long g = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long nseg = (ntiles + seg_len - 1) / seg_len;
+  if (n >= M || g >= nseg) return;
+  const long long t0 = g * seg_len;
+  const long long t1 = t0 + seg_len < ntiles ? t0 + seg_len : ntiles;
+  const double* src = tile_buf + (size_t)blockIdx.y * ntiles * M * W;
+  double* dst = tile_start + (size_t)blockIdx.y * ntiles * M * SW;
+  State s;
+  Elem::load_state(s, seg_start + (((size_t)blockIdx.y * nseg + g) * M + n) * SW);
+  for (long long t = t0; t < t1; ++t) {
+    Map e;
+    Elem::load_map(e, src + ((size_t)t * M + n) * W);
+    Elem::store_state(s, dst + ((size_t)t * M + n) * SW);
+    Elem::apply(e, s);
+  }
 }
 
 // The shard's single aggregate (composition of its tiles in processing order): what a GPU
@@ -193,15 +276,12 @@ __global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const De
   const long long chunk = first + c;
   if (n >= M || chunk >= nchunks) return;
   Elem el(P, St, n, a);
+  el.begin_apply();
   State s;
   Elem::load_state(s, s_state + ((size_t)c * M + n) * SW);
   const long long s0 = chunk * kScanSteps;
   const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
-  if (s0 + 1 < a.nsteps) el.prefetch(a.kfirst + a.dir * (s0 + 1));
-  for (long long t = s0; t < s1; ++t) {
-    if (t + 2 < a.nsteps) el.prefetch(a.kfirst + a.dir * (t + 2));
-    el.step(a.kfirst + a.dir * t, s);
-  }
+  scan_walk(el, a, s0, s1, [&](long long k, const typename Elem::In& in, const typename Elem::Tab& tb) { el.step(k, in, tb, s); });
   el.finish_apply();
 }
 
