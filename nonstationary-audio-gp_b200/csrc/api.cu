@@ -21,6 +21,7 @@
 #include "adfcta.cuh"
 #include "ekf.cuh"
 #include "ekfscan.cuh"
+#include "ekfbig.cuh"
 #include "mcrec.cuh"
 #include "comm.cuh"
 #include "siteupd.cuh"

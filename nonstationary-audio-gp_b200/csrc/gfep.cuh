@@ -225,16 +225,19 @@ struct RtsElem {
     mat_mul<BM>(A, s.PSk, AP);
     mat_mul_bt_add<BM>(AP, A, Q, s.PSkp);               // :213
     // Cholesky PSkp = L L' (lower), padding rows/cols treated as identity (:216)
-    double L[BM * BM];
+    double L[BM * BM], Linv[BM];
     s.ok = true;
 #pragma unroll
     for (int j = 0; j < BM; ++j) {
       double d = (j < b) ? s.PSkp[j + j * BM] : 1.0;
 #pragma unroll
       for (int l = 0; l < BM; ++l) if (l < j) d = fma(-L[j + l * BM], L[j + l * BM], d);
-      if (!(d > 0.0)) { s.ok = false; d = 1.0; }
-      const double ljj = sqrt(d);
-      const double inv = 1.0 / ljj;
+      if (!(d > 0.0) || !(d < 1e300)) { s.ok = false; d = 1.0; }
+      // 1/sqrt(d) once per pivot, straight-line (fastmath.cuh, <= 1 ulp): the triangular solves below multiply by it
+      // instead of dividing 6 BM times by L(j,j) -- the divisions were half of this step's instructions
+      const double inv = rsqrt_fast(d);
+      const double ljj = d * inv;
+      Linv[j] = inv;
       L[j + j * BM] = ljj;
 #pragma unroll
       for (int i = 0; i < BM; ++i) {
@@ -267,7 +270,7 @@ struct RtsElem {
         double v = Bm[i + j * BM];
 #pragma unroll
         for (int l = 0; l < BM; ++l) if (l < j) v = fma(-x[l], L[j + l * BM], v);
-        x[j] = v / L[j + j * BM];
+        x[j] = v * Linv[j];
       }
 #pragma unroll
       for (int jj = 0; jj < BM; ++jj) {                 // g L = x  (backward)
@@ -275,7 +278,7 @@ struct RtsElem {
         double v = x[j];
 #pragma unroll
         for (int l = 0; l < BM; ++l) if (l > j) v = fma(-s.G[i + l * BM], L[l + j * BM], v);
-        s.G[i + j * BM] = v / L[j + j * BM];
+        s.G[i + j * BM] = v * Linv[j];
       }
     }
 #pragma unroll

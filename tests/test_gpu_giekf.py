@@ -158,3 +158,25 @@ def test_giekf_c4_shape_n73_matches_oracle(nsagp, gpu_lib, giekf_form, g_iter):
         assert rel_err(lbg, lbo) < tol and rel_err(ubg, ubo) < tol
         assert rel_err(og["MF"], oo["MF"]) < tol and rel_err(og["MS"], oo["MS"]) < tol
         assert rel_err(og["PF"], oo["PF"]) < tol and rel_err(og["PS"], oo["PS"]) < tol
+
+
+@pytest.mark.parametrize("g_iter", [1, 2])
+def test_giekf_c4_shape_n137_matches_oracle(nsagp, gpu_lib, giekf_form, g_iter):
+    """BASELINE config C4's second shape (D = 32 matern32 subbands, N = 3 matern52 modulators: dense n = 137,
+    cf_matern32_to_ss.m:93-117) with missing-data gaps: the large-state smoother (csrc/ekfbig.cuh, operands in HBM / L2)
+    against the oracle, default chunking and a chunking with several chunks and segments."""
+    from oracle import giekf
+    D, N, T, k1, k2 = 32, 3, 140, "matern32", "matern52"
+    pb = make_problem(nsagp, D, N, T, k1, k2, seed=137, kind="power", p=9, gaps=True, w_lik=1e-2, speech=True)
+    w = pb["hyp"].pack_log()
+    Eo, Vo, _, lbo, ubo, oo = giekf.gf_giekf_modulator_nmf(w, pb["t"], pb["y"], pb["ss_ref"], None, pb["t"], k1, k2, 1, D, N,
+                                                           g_iter, 1, want_cov=True)
+    assert oo["MS"].shape[0] == 137
+    for cl, sc in ((0, 0), (9, 4)):
+        giekf_form(0 if cl == 0 else 2, cl, sc)
+        Eg, Vg, _, lbg, ubg, og = nsagp.gf_giekf_modulator_nmf(w, pb["t"], pb["y"], pb["ss_gpu"], None, pb["t"], k1, k2, 1, D, N,
+                                                               g_iter, 1, debug_cov=True)
+        assert rel_err(og["MF"], oo["MF"]) < TOL and rel_err(og["PF"], oo["PF"]) < TOL          # the sequential filter
+        assert rel_err(Eg, Eo) < 1e-6 and rel_err(Vg, Vo) < 1e-6
+        assert rel_err(lbg, lbo) < 1e-6 and rel_err(ubg, ubo) < 1e-6
+        assert rel_err(og["MS"], oo["MS"]) < 1e-6 and rel_err(og["PS"], oo["PS"]) < 1e-6
