@@ -281,6 +281,15 @@ int nsagp_plan_run_chunked(nsagp_plan* plan, nsagp_comm* comm);
  * out2[1] = max |stored mean| there.  chunks <= 1: the exact sequential pass (default). */
 int nsagp_plan_set_adf_parallel(nsagp_plan* plan, int32_t chunks, int64_t burnin);
 int nsagp_plan_adf_mismatch(nsagp_plan* plan, double* out2);
+/* Stationary (infinite-horizon) Kalman filter / RTS smoother of the probabilistic filter bank, the step that
+ * initialises the subbands before the EP path: the two time loops of
+ * matlab/unifying_prob_tf/kernel_ss_kalmanFastFB.m:86-147.  The caller keeps the reference's `dare` calls (:50, :131)
+ * and passes the constant matrices, all n-by-n column-major: A, AKHA = A - K H A (:63), the gain Kg = K (:60, n),
+ * HA = H A (:77, n), the innovation variance S (:53), and -- for the smoother, NULL = filter only (KF = 1) -- the
+ * smoother gain G (:126).  y[T] with NaN = missing (:103-106).  Out: MS n-by-T (filtered or smoothed means, :109/:146)
+ * and lik_quad = sum over observed steps of v^2 / (2 S) (:99); the caller adds the constant part (:80). */
+int nsagp_fastfb(int32_t n, const double* A, const double* AKHA, const double* Kg, const double* HA, double S,
+                 const double* G, const double* y, int64_t T, double* MS, double* lik_quad);
 /* Device time (ms, CUDA events on the launch stream) of the phases of the last
  * nsagp_plan_run: [0] total, [1] ADF filter pass, [2] fixed-site filter passes,
  * [3] smoother passes, [4] site-update passes.  Returns the number written. */

@@ -1,8 +1,8 @@
 function [varargout] = gf_ep_modulator_nmf(w,x,y,ss,mom,xt,kernel1,kernel2,num_lik_params,D,N,ep_fraction,ep_damping,ep_itts)
 % GF_EP_MODULATOR_NMF - drop-in for matlab/gf_ep_modulator_nmf.m (full-state Power EP:
 % Kalman filter, RTS smoother, site updates) with the time loops on a B200.
-% `mom` must come from nsagp_mom.  The model is NOT balanced here, as in the reference (:80).
-  if ~isstruct(mom), error('nsagp:mom', 'build `mom` with nsagp_mom(...)'); end
+% `mom`: the reference's closure or an nsagp_mom descriptor (nsagp_resolve_mom).  The model is NOT balanced here, as in the reference (:80).
+  mom = nsagp_resolve_mom(mom, N);      % the reference's own closure (or an nsagp_mom descriptor)
   [yall, return_ind] = nsagp_merge(x, y, xt);
   lik_param = w(1:num_lik_params);
   param1 = exp(w(num_lik_params+1:num_lik_params+3*D));

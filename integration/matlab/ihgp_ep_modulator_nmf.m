@@ -3,11 +3,11 @@ function [varargout] = ihgp_ep_modulator_nmf(w,x,y,ss,mom,xt,kernel1,kernel2,num
 % AaltoML/nonstationary-audio-gp with the time loops on a B200 (libnsagp.so via nsagp_mex).
 %
 % Same arguments and outputs as the reference ({nlZ, grad} when xt is empty, otherwise
-% {Eft, Varft, Covft, lb, ub, out}); the only difference is `mom`, which must be the
-% descriptor returned by nsagp_mom (a function handle cannot run on the GPU).
+% {Eft, Varft, Covft, lb, ub, out}); `mom` may be the reference's own closure
+% (resolved by nsagp_resolve_mom from the variables it captured) or an nsagp_mom descriptor.
 % What stays in MATLAB is what the reference also does once per call with built-ins:
 % merging inputs, unpacking w, ss(...), balance, lti_disc and the DARE tables.
-  if ~isstruct(mom), error('nsagp:mom', 'build `mom` with nsagp_mom(...)'); end
+  mom = nsagp_resolve_mom(mom, N);      % the reference's own closure (or an nsagp_mom descriptor)
   [yall, return_ind] = nsagp_merge(x, y, xt);
   lik_param = w(1:num_lik_params);
   param1 = exp(w(num_lik_params+1:num_lik_params+3*D));

@@ -14,6 +14,7 @@
 //   out = nsagp_mex('giekf_carry', model, W, sigma2, g_iter, l_iter, yall, mode)  (gf_giekf_modulator_nmf.m: m, P carried)
 //   [Esig, Vsig, Eft_mod, Varft_mod] = nsagp_mex('mc_reconstruct', Eft, Varft, W, link_shift, sqrt_model, s, Z_or_seed)
 //   [lZ, dlZ, d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)
+//   [MS, lik_quad] = nsagp_mex('fastfb', A, AKHA, K, HA, S, G_or_empty, y)
 // model  : struct with fields D, N, bz, bg, A, Q, Pinf, h   (packed per-latent blocks, see nsagp_model)
 // lik    : struct with fields kind, sn2, link_shift, W (D-by-N), wn (1-by-S), xn (N-by-S)
 // ep     : struct with fields ep_fraction, ep_damping (vector), ep_itts
@@ -46,17 +47,32 @@ const double* dbl(const mxArray* a, const char* what) {
 
 double scalar(const mxArray* s, const char* name) { return mxGetScalar(field(s, name)); }
 
+// Every array handed to the C ABI is read by element count there: a mis-sized argument must be an error here, not an
+// out-of-bounds read inside MATLAB's address space.
+void need(const mxArray* a, size_t count, const char* what) {
+  const size_t have = a ? mxGetNumberOfElements(a) : 0;
+  if (have != count) mexErrMsgIdAndTxt("nsagp:arg", "%s has %zu elements, expected %zu", what, have, count);
+}
+
 void fill_model(const mxArray* m, nsagp_model* out) {
   out->D = (int32_t)scalar(m, "D"); out->N = (int32_t)scalar(m, "N");
   out->bz = (int32_t)scalar(m, "bz"); out->bg = (int32_t)scalar(m, "bg");
+  if (out->D < 1 || out->N < 1 || out->bz < 1 || out->bz > 8 || out->bg < 1 || out->bg > 8)
+    mexErrMsgIdAndTxt("nsagp:arg", "model: need D, N >= 1 and block sizes in 1..8");
+  const size_t nb = (size_t)out->D * out->bz * out->bz + (size_t)out->N * out->bg * out->bg;
+  const size_t nh = (size_t)out->D * out->bz + (size_t)out->N * out->bg;
+  need(field(m, "A"), nb, "model.A"); need(field(m, "Q"), nb, "model.Q"); need(field(m, "Pinf"), nb, "model.Pinf");
+  need(field(m, "h"), nh, "model.h");
   out->A = dbl(field(m, "A"), "model.A"); out->Q = dbl(field(m, "Q"), "model.Q");
   out->Pinf = dbl(field(m, "Pinf"), "model.Pinf"); out->h = dbl(field(m, "h"), "model.h");
 }
 
-void fill_lik(const mxArray* l, nsagp_lik* out) {
+void fill_lik(const mxArray* l, nsagp_lik* out, int32_t D, int32_t N) {
   out->kind = (int32_t)scalar(l, "kind"); out->sn2 = scalar(l, "sn2"); out->link_shift = scalar(l, "link_shift");
-  out->W = dbl(field(l, "W"), "lik.W");
   out->S = (int32_t)mxGetNumberOfElements(field(l, "wn"));
+  need(field(l, "W"), (size_t)D * N, "lik.W");
+  need(field(l, "xn"), (size_t)N * out->S, "lik.xn");
+  out->W = dbl(field(l, "W"), "lik.W");
   out->wn = dbl(field(l, "wn"), "lik.wn"); out->xn = dbl(field(l, "xn"), "lik.xn");
 }
 
@@ -80,7 +96,7 @@ void ep_call(bool ihgp, int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs
   (void)nlhs;
   nsagp_model model; nsagp_lik lik; nsagp_ep ep; nsagp_tables tab;
   fill_model(prhs[1], &model);
-  fill_lik(prhs[2], &lik);
+  fill_lik(prhs[2], &lik, model.D, model.N);
   ep.ep_fraction = scalar(prhs[3], "ep_fraction");
   ep.ep_itts = (int32_t)scalar(prhs[3], "ep_itts");
   ep.ep_damping = dbl(field(prhs[3], "ep_damping"), "ep.ep_damping");
@@ -91,6 +107,9 @@ void ep_call(bool ihgp, int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs
     tab.r = dbl(field(prhs[4], "r"), "tables.r");
     tab.PP = dbl(field(prhs[4], "PP"), "tables.PP");
     tab.PG = dbl(field(prhs[4], "PG", false), "tables.PG");
+    const size_t nb2 = (size_t)model.D * model.bz * model.bz + (size_t)model.N * model.bg * model.bg;
+    need(field(prhs[4], "PP"), (size_t)tab.nr * nb2, "tables.PP");
+    if (tab.PG) need(field(prhs[4], "PG", false), (size_t)tab.nr * 2 * nb2, "tables.PG");
   }
   const double* y = dbl(prhs[5], "yall");
   const int64_t T = (int64_t)mxGetNumberOfElements(prhs[5]);
@@ -127,6 +146,7 @@ void giekf_call(bool carry, int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
   (void)nlhs;
   nsagp_model model;
   fill_model(prhs[1], &model);
+  need(prhs[2], (size_t)model.D * model.N, "W");
   const double* W = dbl(prhs[2], "W");
   const double sigma2 = mxGetScalar(prhs[3]);
   const int32_t g_iter = (int32_t)mxGetScalar(prhs[4]), l_iter = (int32_t)mxGetScalar(prhs[5]);
@@ -157,6 +177,7 @@ void mc_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   const int64_t T = (int64_t)mxGetN(prhs[1]);
   const int32_t s = (int32_t)mxGetScalar(prhs[6]);
   if ((int64_t)mxGetM(prhs[1]) != D + N) mexErrMsgIdAndTxt("nsagp:arg", "Eft must be (D+N)-by-T");
+  need(prhs[2], (size_t)(D + N) * (size_t)T, "Varft");
   const bool seeded = mxGetNumberOfElements(prhs[7]) == 1;
   if (!seeded && (int64_t)mxGetNumberOfElements(prhs[7]) != T * s * (D + N)) mexErrMsgIdAndTxt("nsagp:arg", "Z must be T-by-s-by-(D+N)");
   mxArray* Es = mxCreateDoubleMatrix(T, 1, mxREAL);
@@ -176,9 +197,10 @@ void mc_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
 void mom_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: [lZ,dlZ,d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)");
   nsagp_lik lik;
-  fill_lik(prhs[1], &lik);
   const int32_t D = (int32_t)mxGetScalar(prhs[2]), N = (int32_t)mxGetScalar(prhs[3]);
+  fill_lik(prhs[1], &lik, D, N);
   const int64_t T = (int64_t)mxGetNumberOfElements(prhs[5]);
+  need(prhs[6], (size_t)(D + N) * (size_t)T, "mu"); need(prhs[7], (size_t)(D + N) * (size_t)T, "s2");
   mxArray* lZ = mxCreateDoubleMatrix(1, T, mxREAL);
   mxArray* d1 = mxCreateDoubleMatrix(D + N, T, mxREAL);
   mxArray* d2 = mxCreateDoubleMatrix(D + N, T, mxREAL);
@@ -187,6 +209,23 @@ void mom_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   plhs[0] = lZ;
   if (nlhs > 1) plhs[1] = d1; else mxDestroyArray(d1);
   if (nlhs > 2) plhs[2] = d2; else mxDestroyArray(d2);
+}
+
+// [MS, lik_quad] = nsagp_mex('fastfb', A, AKHA, K, HA, S, G_or_empty, y)   (kernel_ss_kalmanFastFB.m:86-147)
+void fastfb_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs != 8) mexErrMsgIdAndTxt("nsagp:arg", "usage: [MS, lik_quad] = nsagp_mex('fastfb', A, AKHA, K, HA, S, G, y)");
+  const int32_t n = (int32_t)mxGetM(prhs[1]);
+  const size_t nn = (size_t)n * n;
+  need(prhs[1], nn, "A"); need(prhs[2], nn, "AKHA"); need(prhs[3], (size_t)n, "K"); need(prhs[4], (size_t)n, "HA");
+  const bool smooth = !mxIsEmpty(prhs[6]);
+  if (smooth) need(prhs[6], nn, "G");
+  const int64_t T = (int64_t)mxGetNumberOfElements(prhs[7]);
+  mxArray* MS = mxCreateDoubleMatrix(n, T, mxREAL);
+  double quad = 0.0;
+  check(nsagp_fastfb(n, dbl(prhs[1], "A"), dbl(prhs[2], "AKHA"), dbl(prhs[3], "K"), dbl(prhs[4], "HA"), mxGetScalar(prhs[5]),
+                     smooth ? dbl(prhs[6], "G") : nullptr, dbl(prhs[7], "y"), T, mxGetDoubles(MS), &quad));
+  plhs[0] = MS;
+  if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(quad);
 }
 
 }  // namespace
@@ -202,6 +241,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   else if (c == "giekf_carry") giekf_call(true, nlhs, plhs, nrhs, prhs);
   else if (c == "mc_reconstruct") mc_call(nlhs, plhs, nrhs, prhs);
   else if (c == "mom") mom_call(nlhs, plhs, nrhs, prhs);
+  else if (c == "fastfb") fastfb_call(nlhs, plhs, nrhs, prhs);
   else if (c == "version") plhs[0] = mxCreateString(nsagp_version());
   else mexErrMsgIdAndTxt("nsagp:arg", "unknown command '%s'", cmd);
 }

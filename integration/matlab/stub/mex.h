@@ -21,6 +21,7 @@ size_t mxGetNumberOfElements(const mxArray*);
 size_t mxGetM(const mxArray*);
 size_t mxGetN(const mxArray*);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
+mxArray* mxCreateDoubleScalar(double);
 mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
 mxArray* mxCreateString(const char*);
 int mxAddField(mxArray*, const char*);

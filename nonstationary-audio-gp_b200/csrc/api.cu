@@ -25,6 +25,7 @@
 #include "mcrec.cuh"
 #include "comm.cuh"
 #include "siteupd.cuh"
+#include "fastfb.cuh"
 
 using namespace nsagp;
 
@@ -1115,6 +1116,7 @@ int plan_reset(nsagp_plan* pl) {
 #include "api_ekf.inc"
 #include "api_chunk.inc"
 #include "api_comm.inc"
+#include "api_fb.inc"
 #include "api_tables.inc"
 #include "api_mc.inc"
 
