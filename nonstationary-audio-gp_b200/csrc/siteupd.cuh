@@ -26,16 +26,18 @@ namespace nsagp {
 
 constexpr int kSiteSteps = 32;       // steps per CTA
 constexpr int kSiteThreads = 4 * kSiteSteps;
+constexpr int kSiteRow = 33;         // doubles per step of the cavity rows: odd, so the 8 steps of a warp hit 8 different banks
+__host__ __device__ inline int site_tab_stride(int ndist) { return (2 * kNP * ndist) | 1; }   // the same for the link table
 
 // shared-memory doubles
 __host__ __device__ inline int site4_smem_doubles(int M, int S, int ndist, bool full) {
   int o = 0;
   o += (full ? 5 : 4) * kSiteSteps * M;                 // E, tt, tn, R (ihgp) | V, Rout (full)
-  o += 2 * kSiteSteps * 32;                             // cavity mean / variance, rows padded to 32
+  o += 2 * kSiteSteps * kSiteRow;                       // cavity mean / variance, one padded row per step
   o += 2 * kSiteSteps * kNP;                            // sd, 1/s2 of the modulators
   o += 2 * kSiteSteps;                                  // y, lZ
   o += S + kNP * S;                                     // wn, xn
-  o += 2 * kSiteSteps * kNP * (ndist > 0 ? ndist : 0);  // link table
+  o += ndist > 0 ? kSiteSteps * site_tab_stride(ndist) : 0;   // link table
   o += (kNP * S + 7) / 8;                               // index map (bytes)
   return o;
 }
@@ -60,15 +62,15 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   double* s_R = s_tn + kSiteSteps * M;                  // ihgp: R (in/out); full: V (in)
   double* s_Ro = s_R + kSiteSteps * M;                  // full: R (out)
   double* s_mu = s_Ro + (FULL ? kSiteSteps * M : 0);
-  double* s_s2 = s_mu + kSiteSteps * 32;
-  double* s_sd = s_s2 + kSiteSteps * 32;
+  double* s_s2 = s_mu + kSiteSteps * kSiteRow;
+  double* s_sd = s_s2 + kSiteSteps * kSiteRow;
   double* s_rs2 = s_sd + kSiteSteps * kNP;
   double* s_y = s_rs2 + kSiteSteps * kNP;
   double* s_lz = s_y + kSiteSteps;
   double* s_wn = s_lz + kSiteSteps;
   double* s_xn = s_wn + S;
   double* s_tab = s_xn + kNP * S;                       // [step][kNP][nd][2] = (x, link(x))
-  unsigned char* s_xi = reinterpret_cast<unsigned char*>(s_tab + 2 * kSiteSteps * kNP * (nd > 0 ? nd : 0));
+  unsigned char* s_xi = reinterpret_cast<unsigned char*>(s_tab + (nd > 0 ? kSiteSteps * site_tab_stride(nd) : 0));
 
   // ---- phase A: rows in, cavities ------------------------------------------------------------------------------
   for (int i = tid; i < S; i += kSiteThreads) s_wn[i] = P.wn[i];
@@ -92,8 +94,8 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     s_E[i] = mm; s_tt[i] = tt; s_tn[i] = tn;
     const double vcav = 1.0 / (1.0 / vm - alpha * tt);                      // ihgp :407, gf_ep :248
     const double mcav = vcav * (mm / vm - alpha * tn);                      // ihgp :408, gf_ep :249
-    s_mu[gi * 32 + n] = mcav;
-    s_s2[gi * 32 + n] = vcav;
+    s_mu[gi * kSiteRow + n] = mcav;
+    s_s2[gi * kSiteRow + n] = vcav;
     if (n >= D) {
       s_sd[gi * kNP + n - D] = sqrt(vcav);          // NaN for a negative cavity variance (the reference goes complex)
       s_rs2[gi * kNP + n - D] = 1.0 / vcav;
@@ -112,16 +114,16 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     const bool in = d < D;
 #pragma unroll
     for (int j = 0; j < kNP; ++j) W[i][j] = in ? P.W[d * kNP + j] : 0.0;
-    muz[i] = (in && valid) ? s_mu[g * 32 + d] : 0.0;
-    s2z[i] = (in && valid) ? s_s2[g * 32 + d] : 0.0;
+    muz[i] = (in && valid) ? s_mu[g * kSiteRow + d] : 0.0;
+    s2z[i] = (in && valid) ? s_s2[g * kSiteRow + d] : 0.0;
   }
-  const double mug = valid ? s_mu[g * 32 + D + jj] : 0.0;
+  const double mug = valid ? s_mu[g * kSiteRow + D + jj] : 0.0;
   const double sdg = valid ? s_sd[g * kNP + jj] : 1.0;
   const double rs2g = valid ? s_rs2[g * kNP + jj] : 1.0;
   const double yv = valid ? y : 0.0;
   const double noise = P.sn2 / alpha;
   const double shift = P.link_shift;
-  double* tabg = s_tab + (size_t)g * kNP * nd * 2;
+  double* tabg = s_tab + (size_t)g * site_tab_stride(nd);
   if (nd > 0) {
     if (dg < N) {
       for (int q = 0; q < nd; ++q) {
@@ -212,11 +214,11 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     const double d1 = zp * r1;
     const double d2 = -d1 * d1 + zp * r2;
     const int o = g * M + n;
-    const double vcav = s_s2[g * 32 + n];
+    const double vcav = s_s2[g * kSiteRow + n];
     double tt = s_tt[o];
     const bool upd = vcav > 0.0;                    // ihgp :411
     if (upd) {
-      const double mcav = s_mu[g * 32 + n];
+      const double mcav = s_mu[g * kSiteRow + n];
       const double den = 1.0 + d2 * vcav;
       tt = keep * tt + ep_damp * (-d2 / den);                                  // :428
       s_tn[o] = keep * s_tn[o] + ep_damp * ((d1 - mcav * d2) / den);           // :430

@@ -54,6 +54,8 @@ FULL_METRICS = [
     ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "FP64 tensor (DMMA) pipe % (active SMs)"),
     ("sm__ops_path_tensor_src_fp64.sum.per_second", "FP64 tensor ops/ns, chip (peak 37170)"),
     ("sm__ops_path_tensor_src_fp64.sum.pct_of_peak_sustained_elapsed", "FP64 tensor ops % of peak"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 sector hit rate"),
+    ("lts__t_sector_hit_rate.pct", "L2 sector hit rate"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory wavefronts % of peak"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
@@ -64,7 +66,12 @@ FULL_METRICS = [
 
 
 def full(src, dst, cmd):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # src: a .ncu-rep, or the CSV `ncu -i X.ncu-rep --page raw --csv` wrote on the GPU box (the reports themselves
+    # are too large to bring back: gpurun_out/ is limited to 64 MiB)
+    if src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}

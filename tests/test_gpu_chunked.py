@@ -206,12 +206,12 @@ def test_parallel_adf_sharded_over_ranks(nsagp, gpu_lib, kind):
     got = _assemble(plans, ranges, names)
     for k in ("Eft", "R", "MF", "MS"):
         assert rel_err(got[k], ref[k]) < 1e-6, k
-    # sites: element-wise (a smoother-side update with 1 + d2lZ * v_cav ~ 0 yields ttau ~ 1e13 and amplifies the
-    # 1e-13 deviation of the first pass by as much; such a site is a pure "R = 0" site for everything downstream,
-    # and a max-norm comparison would see nothing else)
-    for k in ("ttau", "tnu"):
-        ok = np.abs(ref[k]) < 1e6
-        assert ok.mean() > 0.999 and np.allclose(got[k][ok], ref[k][ok], rtol=1e-6, atol=1e-9), k
+    # sites through what the passes consume, R = 1/ttau (above) and the pseudo-observation tnu/ttau: a smoother-side
+    # update with 1 + d2lZ * v_cav ~ 0 yields ttau ~ 1e13 and amplifies the 1e-13 deviation of the first pass by as much
+    # in ttau and tnu themselves, while R and tnu/ttau of such a site stay well conditioned
+    pos = ref["ttau"] > 0
+    assert np.array_equal(got["ttau"] > 0, pos)
+    assert rel_err((got["tnu"] / got["ttau"])[pos], (ref["tnu"] / ref["ttau"])[pos]) < 1e-6
     for r in range(world):
         assert rel_err(got["nlZ"][r], ref["nlZ"]) < 1e-8
         mis, scale = plans[r].adf_mismatch()
