@@ -196,11 +196,20 @@ def test_parallel_adf_sharded_over_ranks(nsagp, gpu_lib, kind):
     through the device-side exchange: against the exact single-plan run."""
     T, itts, world = 24000, 3, 3
     damping = np.linspace(0.3, 0.2, itts)
-    pb = _short_memory_problem(nsagp, 6, 3, T, 12, kind)
     names = ("Eft", "ttau", "tnu", "R", "MF", "MS", "nlZ")
-    single = _plans(nsagp, pb, itts, damping, 1, kind)[0]
-    single.run()
-    ref = single.fetch(0, names)
+    # A smoother-side site update with 1 + d2lZ * v_cav ~ 0 (seed 12 has one: ttau = 1.8e13) is singular in the
+    # reference itself: the SIGN of its denominator, hence whether the site ends at 1e13 or is clamped to 0, flips with
+    # a 1e-13 perturbation.  Such a step says nothing about the parallel first pass; take a signal without one.
+    for seed in range(12, 40):
+        pb = _short_memory_problem(nsagp, 6, 3, T, seed, kind)
+        single = _plans(nsagp, pb, itts, damping, 1, kind)[0]
+        single.run()
+        ref = single.fetch(0, names)
+        if np.max(np.abs(ref["ttau"])) < 1e6:
+            break
+        single.close()
+    else:
+        pytest.skip("no well-conditioned signal found")
     plans = _plans(nsagp, pb, itts, damping, world, kind)
     ranges, cms = _run_threads(nsagp, plans, par=(4, 2500))
     got = _assemble(plans, ranges, names)
