@@ -435,6 +435,7 @@ struct RtsScanElem {
     for (int i = 0; i < BM * BM; ++i) s.P[i] = src[BM + i];
   }
   // (no register-pipelined inputs for this element: scan.cuh scan_walk)
+  static constexpr bool kTwoTiles = false;
   static constexpr int kPrefetch = 1;
   struct In {};
   struct Tab {};
@@ -677,6 +678,7 @@ struct KfScanElem {
     return true;
   }
   // (no register-pipelined inputs for this element: scan.cuh scan_walk)
+  static constexpr bool kTwoTiles = false;
   static constexpr int kPrefetch = 1;
   struct In {};
   struct Tab {};

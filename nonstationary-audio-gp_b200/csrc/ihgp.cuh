@@ -241,6 +241,7 @@ struct AffineElemBase {
   using State = MeanState<BM>;
   static constexpr int kMapDoubles = BM * BM + BM;
   static constexpr int kStateDoubles = BM;
+  static constexpr bool kTwoTiles = BM <= 4;       // scan.cuh ScanBounds: two CTA tiles per SM (register cap 102)
   __device__ static __forceinline__ void compose(Map& acc, const Map& e) { affine_compose<BM>(acc, e); }
   __device__ static __forceinline__ void apply(const Map& e, State& s) { affine_apply<BM>(e, s.m); }
   __device__ static __forceinline__ void store_map(const Map& e, double* dst) {

@@ -76,8 +76,17 @@ __device__ __forceinline__ void scan_walk(Elem& el, const ScanArgs& a, long long
   }
 }
 
+// Launch bounds of the two streaming phases: elements whose walk fits ~100 registers ask for two CTA tiles per SM
+// (kScanThreads2 threads each); the host caps the tile at that many threads (api.cu: scan_setup).
+constexpr int kScanThreads2 = 320;
+template <class Elem> struct ScanBounds {
+  static constexpr int kThreads = Elem::kTwoTiles ? kScanThreads2 : 256;     // 256 x 1: the full-state elements keep their 190-255 registers
+  static constexpr int kMinBlocks = Elem::kTwoTiles ? 2 : 1;
+};
+
 template <class Elem>
-__global__ void scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+__global__ void __launch_bounds__(ScanBounds<Elem>::kThreads, ScanBounds<Elem>::kMinBlocks)
+scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
                                    ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf) {
   using Map = typename Elem::Map;
   constexpr int W = Elem::kMapDoubles;
@@ -239,7 +248,8 @@ scan_total_kernel(const DevProblem* __restrict__ probs, ScanArgs a, const double
 }
 
 template <class Elem>
-__global__ void scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+__global__ void __launch_bounds__(ScanBounds<Elem>::kThreads, ScanBounds<Elem>::kMinBlocks)
+scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
                                   ScanArgs a, const double* __restrict__ chunk_buf,
                                   const double* __restrict__ tile_start) {
   using Map = typename Elem::Map;
