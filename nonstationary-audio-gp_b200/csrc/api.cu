@@ -12,6 +12,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -889,76 +890,107 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
 
 // Geometry of the three-phase scan (scan.cuh): CH chunks of kScanSteps steps per CTA tile, limited
 // by the shared memory the tile needs for its chunk aggregates.
-int scan_ch(const nsagp_plan* pl, int map_doubles, int max_threads) {
+int scan_ch(const nsagp_plan* pl, int map_doubles, int max_threads, int lat) {
   const size_t per_chunk = (size_t)pl->M * map_doubles * sizeof(double);
-  int ch = std::min(16, std::max(1, max_threads / pl->M));   // (latent, chunk) threads of a CTA tile
+  int ch = std::min(16, std::max(1, max_threads / lat));     // (latent, chunk) threads of a CTA tile
   while (ch > 1 && per_chunk * ch > 80 * 1024) --ch;         // phase 3 stages maps + states: < 2x this
   return ch;
 }
 
-template <class Elem>
+// The two latent families of a scan (scan.cuh): subbands compute with bz, modulators with bg; storage stays padded to BM.
+template <class EZ_, class EG_> struct ElemPair { using EZ = EZ_; using EG = EG_; };
+
+// Specialised pairs for the block-size combinations of the reference's kernels that matter (exp / matern32 / matern52
+// subbands with matern52 modulators); everything else computes both families at the padded size.
+#define DISPATCH_FAM(PL, ELEMT, ...)                                                                           \
+  do {                                                                                                         \
+    const int bm_ = (PL)->BM, bz_ = (PL)->bz, bg_ = (PL)->bg;                                                  \
+    if (bm_ == 3 && bz_ == 2 && bg_ == 3) { using Pair_ = ElemPair<ELEMT<3, 2>, ELEMT<3, 3>>; __VA_ARGS__; }    \
+    else if (bm_ == 4 && bz_ == 4 && bg_ == 3) { using Pair_ = ElemPair<ELEMT<4, 4>, ELEMT<4, 3>>; __VA_ARGS__; } \
+    else if (bm_ == 6 && bz_ == 6 && bg_ == 3) { using Pair_ = ElemPair<ELEMT<6, 6>, ELEMT<6, 3>>; __VA_ARGS__; } \
+    else if (bm_ == 2) { using Pair_ = ElemPair<ELEMT<2, 2>, ELEMT<2, 2>>; __VA_ARGS__; }                       \
+    else if (bm_ == 3) { using Pair_ = ElemPair<ELEMT<3, 3>, ELEMT<3, 3>>; __VA_ARGS__; }                       \
+    else if (bm_ == 4) { using Pair_ = ElemPair<ELEMT<4, 4>, ELEMT<4, 4>>; __VA_ARGS__; }                       \
+    else if (bm_ == 6) { using Pair_ = ElemPair<ELEMT<6, 6>, ELEMT<6, 6>>; __VA_ARGS__; }                       \
+    else { using Pair_ = ElemPair<ELEMT<8, 8>, ELEMT<8, 8>>; __VA_ARGS__; }                                     \
+  } while (0)
+
+template <class Pair>
 int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags) {
   a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.flags = flags; a.nprev = 0;
-  a.CH = scan_ch(pl, Elem::kMapDoubles, ScanBounds<Elem>::kThreads);
+  a.CH = scan_ch(pl, Pair::EZ::kMapDoubles, ScanBounds<typename Pair::EZ>::kThreads, std::is_same<typename Pair::EZ, typename Pair::EG>::value ? pl->M : std::max(pl->D, pl->N));
   // a CTA tile of M*CH threads must fit an SM (registers, shared memory): ask the occupancy calculator
+  // a CTA tile of (family latents)*CH threads must fit an SM (registers, shared memory): ask the occupancy calculator
+  // for both families' kernels -- they share the tile geometry, because they share the buffers
   auto fits = [&](int ch) {
-    const size_t sm1 = (size_t)ch * pl->M * Elem::kMapDoubles * sizeof(double);
-    const size_t sm3 = (size_t)ch * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
-    if (sm1 > 48 * 1024) cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-    if (sm3 > 48 * 1024) cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
-    // (a maximal shared-memory carveout was measured 25 % SLOWER for the mean scans: they live on their 90 % L1 hit rate)
-    int n1 = 0, n3 = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, scan_reduce_kernel<Elem>, pl->M * ch, sm1) != cudaSuccess) n1 = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, scan_apply_kernel<Elem>, pl->M * ch, sm3) != cudaSuccess) n3 = 0;
-    cudaGetLastError();
-    return n1 >= 1 && n3 >= 1;
+    auto ok = [&](auto red, auto app, int lat) {
+      const size_t sm1 = (size_t)ch * lat * Pair::EZ::kMapDoubles * sizeof(double);
+      const size_t sm3 = (size_t)ch * lat * (Pair::EZ::kStateDoubles + Pair::EZ::kMapDoubles) * sizeof(double);
+      if (sm1 > 48 * 1024) cudaFuncSetAttribute(red, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+      if (sm3 > 48 * 1024) cudaFuncSetAttribute(app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+      int n1 = 0, n3 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, red, lat * ch, sm1) != cudaSuccess) n1 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, app, lat * ch, sm3) != cudaSuccess) n3 = 0;
+      cudaGetLastError();
+      return n1 >= 1 && n3 >= 1;
+    };
+    if (std::is_same<typename Pair::EZ, typename Pair::EG>::value)
+      return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->M);
+    return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->D) &&
+           ok(scan_reduce_kernel<typename Pair::EG>, scan_apply_kernel<typename Pair::EG>, pl->N);
   };
   while (a.CH > 1 && !fits(a.CH)) --a.CH;
   return NSAGP_OK;
 }
 
 // phase 1 (+ the shard aggregate on request: agg_host [M][W])
-template <class Elem>
+template <class Pair>
 int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  const dim3 block(pl->M, a.CH);          // one thread per (latent, chunk): M <= 32 lanes in x, no warp-level operations in the scans
   const dim3 grid((unsigned)ntiles, pl->B);
-  const size_t sm1 = (size_t)a.CH * pl->M * Elem::kMapDoubles * sizeof(double);
-  if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(scan_reduce_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  scan_reduce_kernel<Elem><<<grid, block, sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile);
-  LAUNCH_CHECK();
-  if (agg_host) {
-    scan_total_kernel<Elem><<<1, 32, 0, g_stream>>>(pl->d_probs, a, pl->d_tile, pl->d_total);
+  auto launch = [&](auto kern, int n0, int cnt) -> int {
+    if (cnt <= 0) return NSAGP_OK;
+    const size_t sm1 = (size_t)a.CH * cnt * Pair::EZ::kMapDoubles * sizeof(double);
+    if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    kern<<<grid, cnt * a.CH, sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile, n0, cnt);
     LAUNCH_CHECK();
-    CU(cudaMemcpyAsync(agg_host, pl->d_total, (size_t)pl->M * Elem::kMapDoubles * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    return NSAGP_OK;
+  };
+  int rcl;
+  if (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
+    if ((rcl = launch(scan_reduce_kernel<typename Pair::EZ>, 0, pl->M))) return rcl;
+  } else {
+    if ((rcl = launch(scan_reduce_kernel<typename Pair::EZ>, 0, pl->D)) || (rcl = launch(scan_reduce_kernel<typename Pair::EG>, pl->D, pl->N))) return rcl;
+  }
+  if (agg_host) {
+    scan_total_kernel<typename Pair::EZ, typename Pair::EG><<<1, 32, 0, g_stream>>>(pl->d_probs, a, pl->d_tile, pl->d_total);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(agg_host, pl->d_total, (size_t)pl->M * Pair::EZ::kMapDoubles * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
   }
   return NSAGP_OK;
 }
 
 // phases 2 and 3; prev_host: nprev aggregates [nprev][M][W] of the shards processed before this one
-template <class Elem>
+template <class Pair>
 int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev, bool prev_on_device = false) {
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  const dim3 block(pl->M, a.CH);          // one thread per (latent, chunk): M <= 32 lanes in x, no warp-level operations in the scans
   const dim3 grid((unsigned)ntiles, pl->B);
-  const size_t sm3 = (size_t)a.CH * pl->M * (Elem::kStateDoubles + Elem::kMapDoubles) * sizeof(double);
-  if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(scan_apply_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   if (nprev > 0) {
     if (pl->B != 1 || nprev > kMaxPrevShards) return fail(NSAGP_ERR_INVALID, "time-chunked scans need B = 1 and at most 16 shards");
-    const size_t w = (size_t)pl->M * Elem::kMapDoubles;
+    const size_t w = (size_t)pl->M * Pair::EZ::kMapDoubles;
     if (!prev_on_device)
       CU(cudaMemcpyAsync(pl->d_tile - (size_t)nprev * w, prev_host, (size_t)nprev * w * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   }
   a.nprev = nprev;
   {
-    const size_t per_tile = (size_t)pl->M * Elem::kMapDoubles * sizeof(double);
+    const size_t per_tile = (size_t)pl->M * Pair::EZ::kMapDoubles * sizeof(double);
     const long long nlist = ntiles + nprev;                   // maps the walk passes through (per problem)
     auto carry = [&](const double* maps, double* starts, long long nmaps, long long count) -> int {
       int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)count, (64 * 1024) / per_tile));
       const size_t sm2 = per_tile * batch;
-      if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(scan_carry_kernel<Elem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-      scan_carry_kernel<Elem><<<pl->B, kCarryThreads, sm2, g_stream>>>(pl->d_probs, pl->d_states, a, maps, starts, batch, nmaps);
+      if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(scan_carry_kernel<typename Pair::EZ, typename Pair::EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      scan_carry_kernel<typename Pair::EZ, typename Pair::EG><<<pl->B, kCarryThreads, sm2, g_stream>>>(pl->d_probs, pl->d_states, a, maps, starts, batch, nmaps);
       LAUNCH_CHECK();
       return NSAGP_OK;
     };
@@ -970,36 +1002,50 @@ int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev, 
       int seg_len = (int)std::ceil(std::sqrt((double)nlist));
       const long long nseg = (nlist + seg_len - 1) / seg_len;
       if (nseg > pl->nseg_max) return fail(NSAGP_ERR_INVALID, "internal: segment scratch too small");
-      const double* maps = pl->d_tile - (size_t)nprev * pl->M * Elem::kMapDoubles;
-      double* starts = pl->d_start - (size_t)nprev * pl->M * Elem::kStateDoubles;
+      const double* maps = pl->d_tile - (size_t)nprev * pl->M * Pair::EZ::kMapDoubles;
+      double* starts = pl->d_start - (size_t)nprev * pl->M * Pair::EZ::kStateDoubles;
       const int gy = std::max(1, 128 / pl->M);
       const dim3 sblock(pl->M, gy), sgrid((unsigned)((nseg + gy - 1) / gy), pl->B);
-      carry_seg_reduce_kernel<Elem><<<sgrid, sblock, 0, g_stream>>>(pl->d_probs, maps, pl->d_seg, nlist, seg_len);
+      carry_seg_reduce_kernel<typename Pair::EZ, typename Pair::EG><<<sgrid, sblock, 0, g_stream>>>(pl->d_probs, maps, pl->d_seg, nlist, seg_len);
       LAUNCH_CHECK();
       int rc = carry(pl->d_seg, pl->d_segstart, nseg, nseg);
       if (rc) return rc;
-      carry_seg_apply_kernel<Elem><<<sgrid, sblock, 0, g_stream>>>(pl->d_probs, maps, pl->d_segstart, starts, nlist, seg_len);
+      carry_seg_apply_kernel<typename Pair::EZ, typename Pair::EG><<<sgrid, sblock, 0, g_stream>>>(pl->d_probs, maps, pl->d_segstart, starts, nlist, seg_len);
       LAUNCH_CHECK();
     }
   }
-  scan_apply_kernel<Elem><<<grid, block, sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start);
-  LAUNCH_CHECK();
+  {
+    auto launch = [&](auto kern, int n0, int cnt) -> int {
+      if (cnt <= 0) return NSAGP_OK;
+      const size_t sm3 = (size_t)a.CH * cnt * (Pair::EZ::kStateDoubles + Pair::EZ::kMapDoubles) * sizeof(double);
+      if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+      kern<<<grid, cnt * a.CH, sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start, n0, cnt);
+      LAUNCH_CHECK();
+      return NSAGP_OK;
+    };
+    int rcl;
+    if (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
+      if ((rcl = launch(scan_apply_kernel<typename Pair::EZ>, 0, pl->M))) return rcl;
+    } else {
+      if ((rcl = launch(scan_apply_kernel<typename Pair::EZ>, 0, pl->D)) || (rcl = launch(scan_apply_kernel<typename Pair::EG>, pl->D, pl->N))) return rcl;
+    }
+  }
   return NSAGP_OK;
 }
 
-template <class Elem>
+template <class Pair>
 int run_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags = 0) {
   if (nsteps <= 0) return NSAGP_OK;
   ScanArgs a;
-  int rc = scan_setup<Elem>(pl, a, kfirst, nsteps, dir, init, kinit, flags);
-  if (rc || (rc = scan_reduce<Elem>(pl, a, nullptr))) return rc;
-  return scan_finish<Elem>(pl, a, nullptr, 0);
+  int rc = scan_setup<Pair>(pl, a, kfirst, nsteps, dir, init, kinit, flags);
+  if (rc || (rc = scan_reduce<Pair>(pl, a, nullptr))) return rc;
+  return scan_finish<Pair>(pl, a, nullptr, 0);
 }
 
-template <template <int> class ElemT>
-int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit) {
+template <template <int, int> class ElemT>
+int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags = 0) {
   int rc = NSAGP_OK;
-  DISPATCH_BM(pl->BM, { rc = run_scan<ElemT<BM_>>(pl, kfirst, nsteps, dir, init, kinit); });
+  DISPATCH_FAM(pl, ElemT, { rc = run_scan<Pair_>(pl, kfirst, nsteps, dir, init, kinit, flags); });
   return rc;
 }
 

@@ -204,23 +204,34 @@ struct RtsStep {
   bool ok;
 };
 
-template <int BM>
+// BMS: leading dimension of the blocks in HBM; BM: the size this latent family computes with (ihgp.cuh: AffineElemBase).
+template <int BMS, int BM>
 struct RtsElem {
   const DevProblem& P; const DevState& St; int n, off, b;
   double A[BM * BM], Q[BM * BM], hv[BM];
   __device__ RtsElem(const DevProblem& P_, const DevState& S_, int n_) : P(P_), St(S_), n(n_) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) { A[i] = P.A[n * BM * BM + i]; Q[i] = P.Q[n * BM * BM + i]; }
+    for (int i = 0; i < BM * BM; ++i) {
+      A[i] = P.A[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
+      Q[i] = P.Q[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
+    }
 #pragma unroll
-    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BM + i];
+    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BMS + i];
+  }
+  // the filtered estimate of step k (the only HBM reads of a step: scan.cuh requests them steps ahead)
+  __device__ __forceinline__ void load(long long k, double (&PSk)[BM * BM], double (&ms)[BM]) const {
+    const double* src = St.PS + ((size_t)k * P.M + n) * BMS * BMS;
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) PSk[i] = src[(i % BM) + (i / BM) * BMS];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
   }
   __device__ __forceinline__ void step(long long k, RtsStep<BM>& s) const {
-    const double* src = St.PS + ((size_t)k * P.M + n) * BM * BM;
-#pragma unroll
-    for (int i = 0; i < BM * BM; ++i) s.PSk[i] = src[i];
-#pragma unroll
-    for (int i = 0; i < BM; ++i) s.ms[i] = (i < b) ? St.MS[k * P.n + off + i] : 0.0;
+    load(k, s.PSk, s.ms);
+    compute(s);
+  }
+  __device__ __forceinline__ void compute(RtsStep<BM>& s) const {
     double AP[BM * BM];
     mat_mul<BM>(A, s.PSk, AP);
     mat_mul_bt_add<BM>(AP, A, Q, s.PSkp);               // :213
@@ -398,13 +409,13 @@ struct RtsState {
   double m[BM], P[BM * BM];
 };
 
-template <int BM>
+template <int BMS, int BM = BMS>
 struct RtsScanElem {
   using Map = RtsMap<BM>;
   using State = RtsState<BM>;
-  static constexpr int kMapDoubles = 2 * BM * BM + BM;
-  static constexpr int kStateDoubles = BM * BM + BM;
-  RtsElem<BM> el;
+  static constexpr int kMapDoubles = 2 * BMS * BMS + BMS;       // slot sizes are the same for both families
+  static constexpr int kStateDoubles = BMS * BMS + BMS;
+  RtsElem<BMS, BM> el;
   bool ok;
   double mdM, mdP;
   __device__ RtsScanElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : el(P_, S_, n_), ok(true), mdM(0.0), mdP(0.0) {}
@@ -434,32 +445,46 @@ struct RtsScanElem {
 #pragma unroll
     for (int i = 0; i < BM * BM; ++i) s.P[i] = src[BM + i];
   }
-  // (no register-pipelined inputs for this element: scan.cuh scan_walk)
+  // Inputs of a step -- the filtered covariance block and mean, and (apply phase) the marginals of the previous EP
+  // iteration for the max-diff diagnostics -- are requested kPrefetch steps ahead (scan.cuh: scan_walk): the apply
+  // phase was bound by two exposed HBM round trips per step (issue slots 2-3 % busy, profiles/r2h_*).
   static constexpr bool kTwoTiles = false;
-  static constexpr int kPrefetch = 1;
-  struct In {};
+  static constexpr int kPrefetch = BM <= 2 ? 3 : 2;
+  struct In { double PSk[BM * BM], ms[BM], Eold, Vold; };
   struct Tab {};
-  __device__ __forceinline__ void load(long long, In&) const {}
+  bool applying = false;
+  __device__ __forceinline__ void begin_apply() { applying = true; }
+  __device__ __forceinline__ void load(long long k, In& in) const {
+    el.load(k, in.PSk, in.ms);
+    in.Eold = applying ? el.St.E[k * el.P.M + el.n] : 0.0;
+    in.Vold = applying ? el.St.V[k * el.P.M + el.n] : 0.0;
+  }
   __device__ __forceinline__ void lookup(long long, const In&, Tab&) const {}
-  __device__ __forceinline__ void get(long long k, const In&, const Tab&, Map& e) { get(k, e); }
-  __device__ __forceinline__ void step(long long k, const In&, const Tab&, State& s) { step(k, s); }
-  __device__ __forceinline__ void begin_apply() {}
-  __device__ __forceinline__ void get(long long k, Map& e) {
+  __device__ __forceinline__ void fill(const In& in, RtsStep<BM>& st) const {
+#pragma unroll
+    for (int i = 0; i < BM * BM; ++i) st.PSk[i] = in.PSk[i];
+#pragma unroll
+    for (int i = 0; i < BM; ++i) st.ms[i] = in.ms[i];
+  }
+  __device__ __forceinline__ void get(long long, const In& in, const Tab&, Map& e) {
     RtsStep<BM> st;
-    el.step(k, st);
+    fill(in, st);
+    el.compute(st);
     ok = ok && st.ok;
     el.as_map(st, e);
   }
-  __device__ __forceinline__ void step(long long k, State& s) {
+  __device__ __forceinline__ void step(long long k, const In& in, const Tab&, State& s) {
     RtsStep<BM> st;
-    el.step(k, st);
+    fill(in, st);
+    el.compute(st);
     el.apply_step(st, s.m, s.P);
     const DevProblem& P = el.P; const DevState& St = el.St; const int n = el.n;
 #pragma unroll
     for (int i = 0; i < BM; ++i) if (i < el.b) St.MS[k * P.n + el.off + i] = s.m[i];
-    double* dst = St.PS + ((size_t)k * P.M + n) * BM * BM;
+    // the whole padded block (zeros outside the BM x BM corner): full 32-byte sectors, no read-modify-write in L2
+    double* dst = St.PS + ((size_t)k * P.M + n) * BMS * BMS;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) dst[i] = s.P[i];
+    for (int i = 0; i < BMS * BMS; ++i) dst[i] = ((i % BMS) < BM && (i / BMS) < BM) ? s.P[(i % BMS) + (i / BMS) * BM] : 0.0;
     double e = 0.0, v = 0.0;
 #pragma unroll
     for (int i = 0; i < BM; ++i) {
@@ -469,8 +494,8 @@ struct RtsScanElem {
       for (int j = 0; j < BM; ++j) g = fma(el.hv[j], s.P[j + i * BM], g);
       v = fma(g, el.hv[i], v);
     }
-    mdM = fmax(mdM, fabs(St.E[k * P.M + n] - e));
-    mdP = fmax(mdP, fabs(St.V[k * P.M + n] - v));
+    mdM = fmax(mdM, fabs(in.Eold - e));
+    mdP = fmax(mdP, fabs(in.Vold - v));
     St.E[k * P.M + n] = e;
     St.V[k * P.M + n] = v;
   }
@@ -479,9 +504,9 @@ struct RtsScanElem {
     const DevProblem& P = el.P; const DevState& St = el.St;
 #pragma unroll
     for (int i = 0; i < BM; ++i) s.m[i] = (i < el.b) ? St.MS[kinit * P.n + el.off + i] : 0.0;
-    const double* src = St.PS + ((size_t)kinit * P.M + el.n) * BM * BM;
+    const double* src = St.PS + ((size_t)kinit * P.M + el.n) * BMS * BMS;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) s.P[i] = src[i];
+    for (int i = 0; i < BM * BM; ++i) s.P[i] = src[(i % BM) + (i / BM) * BMS];
   }
   __device__ __forceinline__ void store_final(const State&) {}
   __device__ __forceinline__ void finish_reduce() { if (!ok) atomicCAS(el.St.status, 0, 1); }
@@ -634,21 +659,24 @@ __device__ __forceinline__ void kf_apply(const KfMap<BM>& e, double (&m)[BM], do
   mat_mul_bt_add<BM>(T2, e.A, e.C, Pm);
 }
 
-template <int BM>
+template <int BMS, int BM = BMS>
 struct KfScanElem {
   using Map = KfMap<BM>;
   using State = RtsState<BM>;
-  static constexpr int kMapDoubles = 3 * BM * BM + 2 * BM;
-  static constexpr int kStateDoubles = BM * BM + BM;
+  static constexpr int kMapDoubles = 3 * BMS * BMS + 2 * BMS;   // slot sizes are the same for both families
+  static constexpr int kStateDoubles = BMS * BMS + BMS;
   const DevProblem& P; const DevState& St; int n, off, b; bool nlz;
   double A[BM * BM], Q[BM * BM], hv[BM], hA[BM], Qh[BM], hQh;
   __device__ KfScanElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs& a)
       : P(P_), St(S_), n(n_), nlz((a.flags & 1) != 0) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) { A[i] = P.A[n * BM * BM + i]; Q[i] = P.Q[n * BM * BM + i]; }
+    for (int i = 0; i < BM * BM; ++i) {
+      A[i] = P.A[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
+      Q[i] = P.Q[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
+    }
 #pragma unroll
-    for (int i = 0; i < BM; ++i) { hv[i] = P.h[n * BM + i]; hA[i] = P.hA[n * BM + i]; }
+    for (int i = 0; i < BM; ++i) { hv[i] = P.h[n * BMS + i]; hA[i] = P.hA[n * BMS + i]; }
     mat_vec<BM>(Q, hv, Qh);
     hQh = 0.0;
 #pragma unroll
@@ -668,8 +696,8 @@ struct KfScanElem {
 #pragma unroll
     for (int i = 0; i < BM; ++i) { e.b[i] = d[3 * BM * BM + i]; e.eta[i] = d[3 * BM * BM + BM + i]; }
   }
-  __device__ static __forceinline__ void store_state(const State& s, double* dst) { RtsScanElem<BM>::store_state(s, dst); }
-  __device__ static __forceinline__ void load_state(State& s, const double* src) { RtsScanElem<BM>::load_state(s, src); }
+  __device__ static __forceinline__ void store_state(const State& s, double* dst) { RtsScanElem<BMS, BM>::store_state(s, dst); }
+  __device__ static __forceinline__ void load_state(State& s, const double* src) { RtsScanElem<BMS, BM>::load_state(s, src); }
   // sites of step k as the frozen pass sees them (:159-176; nlZ mode clamps at every step, :425)
   __device__ __forceinline__ bool sites(long long k, double& tt, double& tn) const {
     if (isnan(St.y[k])) { tt = 0.0; tn = 0.0; return false; }                  // :135 no update at all
@@ -692,12 +720,12 @@ struct KfScanElem {
     sites(k, tt, tn);
     if (k == 0) {                                           // prior (0, Pinf), update only (:116-117,:129)
       double W0[BM], s0 = 0.0;
-      const double* Pi = P.Pinf + n * BM * BM;
+      const double* Pi = P.Pinf + n * BMS * BMS;
 #pragma unroll
       for (int i = 0; i < BM; ++i) {
         double w = 0.0;
 #pragma unroll
-        for (int j = 0; j < BM; ++j) w = fma(Pi[i + j * BM], hv[j], w);
+        for (int j = 0; j < BM; ++j) w = fma(Pi[i + j * BMS], hv[j], w);
         W0[i] = w;
       }
 #pragma unroll
@@ -708,7 +736,7 @@ struct KfScanElem {
 #pragma unroll
         for (int i = 0; i < BM; ++i) {
           e.A[i + j * BM] = 0.0; e.J[i + j * BM] = 0.0;
-          e.C[i + j * BM] = fma(-(W0[i] * (tt * rz)), W0[j], Pi[i + j * BM]);
+          e.C[i + j * BM] = fma(-(W0[i] * (tt * rz)), W0[j], Pi[i + j * BMS]);
         }
 #pragma unroll
       for (int i = 0; i < BM; ++i) { e.b[i] = W0[i] * (tn * rz); e.eta[i] = 0.0; }
@@ -766,15 +794,16 @@ struct KfScanElem {
     }
 #pragma unroll
     for (int i = 0; i < BM; ++i) if (i < b) St.MS[k * P.n + off + i] = s.m[i];
-    double* dst = St.PS + ((size_t)k * P.M + n) * BM * BM;
+    // the whole padded block (zeros outside the BM x BM corner): full 32-byte sectors, no read-modify-write in L2
+    double* dst = St.PS + ((size_t)k * P.M + n) * BMS * BMS;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) dst[i] = s.P[i];
+    for (int i = 0; i < BMS * BMS; ++i) dst[i] = ((i % BMS) < BM && (i / BMS) < BM) ? s.P[(i % BMS) + (i / BMS) * BM] : 0.0;
   }
   __device__ __forceinline__ void init(State& s, int, long long) {            // (0, Pinf); step 0 does not predict
 #pragma unroll
     for (int i = 0; i < BM; ++i) s.m[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) s.P[i] = P.Pinf[n * BM * BM + i];
+    for (int i = 0; i < BM * BM; ++i) s.P[i] = P.Pinf[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
   }
   __device__ __forceinline__ void store_final(const State&) {}
   __device__ __forceinline__ void finish_reduce() {}

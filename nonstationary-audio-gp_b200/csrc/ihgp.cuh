@@ -235,13 +235,16 @@ __device__ __forceinline__ void affine_apply(const Affine<BM>& e, double (&m)[BM
 // loads itself and each step would wait for three dependent L2 round trips.
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <int BM>
+// BMS: leading dimension of the per-latent blocks in HBM (the plan pads every block to max(bz, bg)); BM: size the
+// element computes with -- the block size of the latent family the thread belongs to (scan.cuh runs the subband and
+// the modulator family side by side), so a 2 x 2 subband block next to 3 x 3 modulators costs 2 x 2 arithmetic.
+template <int BMS, int BM>
 struct AffineElemBase {
   using Map = Affine<BM>;
   using State = MeanState<BM>;
-  static constexpr int kMapDoubles = BM * BM + BM;
-  static constexpr int kStateDoubles = BM;
-  static constexpr bool kTwoTiles = BM <= 4;       // scan.cuh ScanBounds: two CTA tiles per SM (register cap 102)
+  static constexpr int kMapDoubles = BMS * BMS + BMS;     // slot sizes are the same for both families
+  static constexpr int kStateDoubles = BMS;
+  static constexpr bool kTwoTiles = BMS <= 4;       // scan.cuh ScanBounds: two CTA tiles per SM (register cap 102)
   __device__ static __forceinline__ void compose(Map& acc, const Map& e) { affine_compose<BM>(acc, e); }
   __device__ static __forceinline__ void apply(const Map& e, State& s) { affine_apply<BM>(e, s.m); }
   __device__ static __forceinline__ void store_map(const Map& e, double* dst) {
@@ -267,8 +270,8 @@ struct AffineElemBase {
 };
 
 // Frozen-site filter step k as an affine map of the block mean (:280-304).
-template <int BM>
-struct FilterElem : AffineElemBase<BM> {
+template <int BMS, int BM = BMS>
+struct FilterElem : AffineElemBase<BMS, BM> {
   using Map = Affine<BM>;
   using State = MeanState<BM>;
   const DevProblem& P; const DevState& St; int n, off, b;
@@ -277,9 +280,9 @@ struct FilterElem : AffineElemBase<BM> {
   __device__ FilterElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
+    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
 #pragma unroll
-    for (int i = 0; i < BM; ++i) hA[i] = P.hA[n * BM + i];
+    for (int i = 0; i < BM; ++i) hA[i] = P.hA[n * BMS + i];
   }
   // Inputs of step k: the sites of steps k and k-1 (the look-up uses R(:,k-1), :239); table row of the look-up.
   static constexpr int kPrefetch = 3;
@@ -299,7 +302,7 @@ struct FilterElem : AffineElemBase<BM> {
       const double Rp = (ttp == 0.0) ? INFINITY : in.Rp;
       idx = lookup_filter_hint(P, Rp);
     }
-    const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BM;
+    const double* wrow = P.Wtab + ((size_t)n * (nr + 1) + idx) * BMS;
 #pragma unroll
     for (int i = 0; i < BM; ++i) tb.w[i] = wrow[i];
     tb.HPH = P.HPHtab[(size_t)n * (nr + 1) + idx];
@@ -336,7 +339,7 @@ struct FilterElem : AffineElemBase<BM> {
   }
   __device__ __forceinline__ void init(State& s, int, long long) {            // m carried from the previous smoother pass
 #pragma unroll
-    for (int i = 0; i < BM; ++i) s.m[i] = St.mcarry[n * BM + i];
+    for (int i = 0; i < BM; ++i) s.m[i] = St.mcarry[n * BMS + i];
   }
   __device__ __forceinline__ void store_final(const State&) {}
   __device__ __forceinline__ void finish_reduce() {}
@@ -344,8 +347,8 @@ struct FilterElem : AffineElemBase<BM> {
 };
 
 // RTS mean step k (:379-394): m_k = MS_k + G_k (m_{k+1} - A MS_k).
-template <int BM>
-struct SmootherElem : AffineElemBase<BM> {
+template <int BMS, int BM = BMS>
+struct SmootherElem : AffineElemBase<BMS, BM> {
   using Map = Affine<BM>;
   using State = MeanState<BM>;
   const DevProblem& P; const DevState& St; int n, off, b;
@@ -356,9 +359,9 @@ struct SmootherElem : AffineElemBase<BM> {
   __device__ SmootherElem(const DevProblem& P_, const DevState& S_, int n_, const ScanArgs&) : P(P_), St(S_), n(n_), mdM(0.0) {
     off = P.off[n]; b = P.off[n + 1] - off;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BM * BM + i];
+    for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
 #pragma unroll
-    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BM + i];
+    for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BMS + i];
   }
   // Inputs of step k: R(:,k) (look-up of the smoother gain), the filtered mean, H*MS of the previous iteration.
   static constexpr int kPrefetch = 3;
@@ -372,9 +375,9 @@ struct SmootherElem : AffineElemBase<BM> {
   }
   __device__ __forceinline__ void lookup(long long, const In& in, Tab& tb) const {
     tb.idx = lookup_smoother_hint(P, in.R);
-    const double* G = P.Gtab + ((size_t)n * P.nr + tb.idx) * BM * BM;
+    const double* G = P.Gtab + ((size_t)n * P.nr + tb.idx) * BMS * BMS;
 #pragma unroll
-    for (int i = 0; i < BM * BM; ++i) tb.G[i] = G[i];
+    for (int i = 0; i < BM * BM; ++i) tb.G[i] = G[(i % BM) + (i / BM) * BMS];
   }
   __device__ __forceinline__ void get_impl(long long k, const In& in, const Tab& tb, Map& e, bool commit) {
     double t[BM];

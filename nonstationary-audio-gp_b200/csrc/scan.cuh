@@ -84,48 +84,75 @@ template <class Elem> struct ScanBounds {
   static constexpr int kMinBlocks = Elem::kTwoTiles ? 2 : 1;
 };
 
+// Two latent families: subbands (n < D, block size bz) and modulators (n >= D, block size bg).  Their element types
+// share the slot sizes kMapDoubles / kStateDoubles (padded to max(bz, bg)), so the buffers have ONE layout; the two
+// streaming phases are launched once per family (latents n0 .. n0+cnt-1) with that family's element type -- its own
+// arithmetic size and its own register allocation (2 x 2 subband blocks next to 3 x 3 modulators: 100 instead of 190
+// registers for 84 % of the threads).  The carry kernels handle both families in one launch.
+struct ScanThread {
+  int n, c;
+  bool live;
+  __device__ __forceinline__ ScanThread(int tid, int n0, int cnt, int CH) {
+    c = tid / cnt;
+    n = n0 + (tid - c * cnt);
+    live = tid < CH * cnt;
+  }
+};
+
+template <class Elem>
+__device__ __forceinline__ void scan_reduce_thread(const DevProblem& P, const DevState& St, const ScanArgs& a, int n, int c,
+                                                   long long chunk, double* chunk_slot, double* sm_slot) {
+  using Map = typename Elem::Map;
+  Map acc;
+  Elem el(P, St, n, a);
+  const long long s0 = chunk * kScanSteps;
+  const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
+  bool first = true;
+  scan_walk(el, a, s0, s1, [&](long long k, const typename Elem::In& in, const typename Elem::Tab& tb) {
+    if (first) { el.get(k, in, tb, acc); first = false; }
+    else { Map e; el.get(k, in, tb, e); Elem::compose(acc, e); }
+  });
+  el.finish_reduce();
+  Elem::store_map(acc, chunk_slot);
+  Elem::store_map(acc, sm_slot);
+}
+
+template <class Elem>
+__device__ __forceinline__ void scan_tile_compose_thread(const double* sm, int n, int M, int cnt, double* tile_slot) {
+  using Map = typename Elem::Map;
+  constexpr int W = Elem::kMapDoubles;
+  Map acc, e;
+  Elem::load_map(acc, sm + (size_t)n * W);
+  for (int j = 1; j < cnt; ++j) {
+    Elem::load_map(e, sm + ((size_t)j * M + n) * W);
+    Elem::compose(acc, e);
+  }
+  Elem::store_map(acc, tile_slot);
+}
+
 template <class Elem>
 __global__ void __launch_bounds__(ScanBounds<Elem>::kThreads, ScanBounds<Elem>::kMinBlocks)
 scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                                   ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf) {
-  using Map = typename Elem::Map;
+                   ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf, int n0, int cnt_lat) {
   constexpr int W = Elem::kMapDoubles;
   const DevProblem& P = probs[blockIdx.y];
   const DevState& St = states[blockIdx.y];
-  const int n = threadIdx.x, c = threadIdx.y, M = P.M, CH = a.CH;
-  extern __shared__ double sm[];                 // [CH][M][W]
+  const int M = P.M, CH = a.CH;
+  const ScanThread th(threadIdx.x, n0, cnt_lat, CH);
+  const int n = th.n, c = th.c;
+  extern __shared__ double sm[];                 // [CH][cnt_lat][W]: this family's latents only
   const long long nchunks = scan_num_chunks(a.nsteps);
   const long long ntiles = scan_num_tiles(a.nsteps, CH);
   const long long chunk = (long long)blockIdx.x * CH + c;
-  const bool live = n < M && chunk < nchunks;
-  if (n < M) {
-    Map acc;
-    if (live) {
-      Elem el(P, St, n, a);
-      const long long s0 = chunk * kScanSteps;
-      const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
-      bool first = true;
-      scan_walk(el, a, s0, s1, [&](long long k, const typename Elem::In& in, const typename Elem::Tab& tb) {
-        if (first) { el.get(k, in, tb, acc); first = false; }
-        else { Map e; el.get(k, in, tb, e); Elem::compose(acc, e); }
-      });
-      el.finish_reduce();
-      Elem::store_map(acc, chunk_buf + (((size_t)blockIdx.y * nchunks + chunk) * M + n) * W);
-      Elem::store_map(acc, sm + ((size_t)c * M + n) * W);
-    }
-  }
+  if (th.live && chunk < nchunks)
+    scan_reduce_thread<Elem>(P, St, a, n, c, chunk, chunk_buf + (((size_t)blockIdx.y * nchunks + chunk) * M + n) * W,
+                             sm + ((size_t)c * cnt_lat + (n - n0)) * W);
   __syncthreads();
-  if (c == 0 && n < M) {
+  if (th.live && c == 0) {
     // compose this tile's chunks in processing order
     const long long first = (long long)blockIdx.x * CH;
     const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
-    Map acc, e;
-    Elem::load_map(acc, sm + (size_t)n * W);
-    for (int j = 1; j < cnt; ++j) {
-      Elem::load_map(e, sm + ((size_t)j * M + n) * W);
-      Elem::compose(acc, e);
-    }
-    Elem::store_map(acc, tile_buf + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * W);
+    scan_tile_compose_thread<Elem>(sm, n - n0, cnt_lat, cnt, tile_buf + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * W);
   }
 }
 
@@ -135,15 +162,26 @@ scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
 constexpr int kCarryThreads = 256;
 
 template <class Elem>
+__device__ __forceinline__ void scan_carry_walk(Elem& el, typename Elem::State& s, const double* sm, double* dst, int M, int tid,
+                                                long long t0, int cnt) {
+  using Map = typename Elem::Map;
+  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
+  for (int j = 0; j < cnt; ++j) {
+    Map e;
+    Elem::load_map(e, sm + ((size_t)j * M + tid) * W);
+    Elem::store_state(s, dst + ((size_t)(t0 + j) * M + tid) * SW);
+    Elem::apply(e, s);
+  }
+}
+
+template <class EZ, class EG>
 __global__ void __launch_bounds__(kCarryThreads)
 scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, ScanArgs a,
                   const double* __restrict__ tile_buf, double* __restrict__ tile_start, int batch, long long nmaps) {
-  using Map = typename Elem::Map;
-  using State = typename Elem::State;
-  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
+  constexpr int W = EZ::kMapDoubles, SW = EZ::kStateDoubles;
   const DevProblem& P = probs[blockIdx.x];
   const DevState& St = states[blockIdx.x];
-  const int tid = threadIdx.x, M = P.M;
+  const int tid = threadIdx.x, M = P.M, D = P.D;
   extern __shared__ double sm[];                 // [batch][M][W]
   // When a signal is time-chunked over GPUs, the aggregates of the shards that come earlier in
   // processing order sit in the nprev slots before tile_buf (single-problem plans only): the
@@ -154,25 +192,24 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   const double* src = tile_buf + (size_t)blockIdx.x * ntiles * M * W - back * M * W;
   double* dst = tile_start + (size_t)blockIdx.x * ntiles * M * SW - back * M * SW;
   const bool walker = tid < M;
-  Elem el(P, St, walker ? tid : 0, a);
-  State s;
-  if (walker) el.init(s, a.init, a.kinit);
+  const bool fz = tid < D;
+  EZ elz(P, St, (walker && fz) ? tid : 0, a);
+  EG elg(P, St, (walker && !fz) ? tid : D, a);
+  typename EZ::State sz;
+  typename EG::State sg;
+  if (walker) { if (fz) elz.init(sz, a.init, a.kinit); else elg.init(sg, a.init, a.kinit); }
   for (long long t0 = 0; t0 < ntiles; t0 += batch) {
     const int cnt = (int)((ntiles - t0 < batch) ? ntiles - t0 : batch);
     const size_t words = (size_t)cnt * M * W;
     for (size_t i = tid; i < words; i += kCarryThreads) sm[i] = src[(size_t)t0 * M * W + i];
     __syncthreads();
     if (walker) {
-      for (int j = 0; j < cnt; ++j) {
-        Map e;
-        Elem::load_map(e, sm + ((size_t)j * M + tid) * W);
-        Elem::store_state(s, dst + ((size_t)(t0 + j) * M + tid) * SW);
-        Elem::apply(e, s);
-      }
+      if (fz) scan_carry_walk<EZ>(elz, sz, sm, dst, M, tid, t0, cnt);
+      else scan_carry_walk<EG>(elg, sg, sm, dst, M, tid, t0, cnt);
     }
     __syncthreads();
   }
-  if (walker) el.store_final(s);   // the state after the last step (used by a following tile / rank)
+  if (walker) { if (fz) elz.store_final(sz); else elg.store_final(sg); }   // the state after the last step
 }
 
 // Two-level carry for long signals: the walk above is one application per CTA tile, i.e. nsteps / (32 CH) dependent
@@ -182,43 +219,42 @@ scan_carry_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
 // state entering every tile (carry_seg_apply): 3 sqrt(ntiles) dependent steps instead of ntiles.
 // tile_buf / tile_start point at the FIRST map of the list (including the nprev shard aggregates in front).
 template <class Elem>
-__global__ void carry_seg_reduce_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ tile_buf,
-                                        double* __restrict__ seg_buf, long long ntiles, int seg_len) {
+__device__ __forceinline__ void carry_seg_reduce_thread(const double* src, double* out, int M, int n, long long t0, long long t1) {
   using Map = typename Elem::Map;
   constexpr int W = Elem::kMapDoubles;
-  const int M = probs[blockIdx.y].M, n = threadIdx.x;
-  const long long g = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  const long long nseg = (ntiles + seg_len - 1) / seg_len;
-  if (n >= M || g >= nseg) return;
-  const long long t0 = g * seg_len;
-  const long long t1 = t0 + seg_len < ntiles ? t0 + seg_len : ntiles;
-  const double* src = tile_buf + (size_t)blockIdx.y * ntiles * M * W;
   Map acc, e;
   Elem::load_map(acc, src + ((size_t)t0 * M + n) * W);
   for (long long t = t0 + 1; t < t1; ++t) {
     Elem::load_map(e, src + ((size_t)t * M + n) * W);
     Elem::compose(acc, e);
   }
-  Elem::store_map(acc, seg_buf + (((size_t)blockIdx.y * nseg + g) * M + n) * W);
+  Elem::store_map(acc, out);
 }
 
-template <class Elem>
-__global__ void carry_seg_apply_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ tile_buf,
-                                       const double* __restrict__ seg_start, double* __restrict__ tile_start,
-                                       long long ntiles, int seg_len) {
-  using Map = typename Elem::Map;
-  using State = typename Elem::State;
-  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
-  const int M = probs[blockIdx.y].M, n = threadIdx.x;
+template <class EZ, class EG>
+__global__ void carry_seg_reduce_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ tile_buf,
+                                        double* __restrict__ seg_buf, long long ntiles, int seg_len) {
+  constexpr int W = EZ::kMapDoubles;
+  const int M = probs[blockIdx.y].M, D = probs[blockIdx.y].D, n = threadIdx.x;
   const long long g = (long long)blockIdx.x * blockDim.y + threadIdx.y;
   const long long nseg = (ntiles + seg_len - 1) / seg_len;
   if (n >= M || g >= nseg) return;
   const long long t0 = g * seg_len;
   const long long t1 = t0 + seg_len < ntiles ? t0 + seg_len : ntiles;
   const double* src = tile_buf + (size_t)blockIdx.y * ntiles * M * W;
-  double* dst = tile_start + (size_t)blockIdx.y * ntiles * M * SW;
+  double* out = seg_buf + (((size_t)blockIdx.y * nseg + g) * M + n) * W;
+  if (n < D) carry_seg_reduce_thread<EZ>(src, out, M, n, t0, t1);
+  else carry_seg_reduce_thread<EG>(src, out, M, n, t0, t1);
+}
+
+template <class Elem>
+__device__ __forceinline__ void carry_seg_apply_thread(const double* src, const double* start, double* dst, int M, int n,
+                                                       long long t0, long long t1) {
+  using Map = typename Elem::Map;
+  using State = typename Elem::State;
+  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
   State s;
-  Elem::load_state(s, seg_start + (((size_t)blockIdx.y * nseg + g) * M + n) * SW);
+  Elem::load_state(s, start);
   for (long long t = t0; t < t1; ++t) {
     Map e;
     Elem::load_map(e, src + ((size_t)t * M + n) * W);
@@ -227,72 +263,103 @@ __global__ void carry_seg_apply_kernel(const DevProblem* __restrict__ probs, con
   }
 }
 
+template <class EZ, class EG>
+__global__ void carry_seg_apply_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ tile_buf,
+                                       const double* __restrict__ seg_start, double* __restrict__ tile_start,
+                                       long long ntiles, int seg_len) {
+  constexpr int W = EZ::kMapDoubles, SW = EZ::kStateDoubles;
+  const int M = probs[blockIdx.y].M, D = probs[blockIdx.y].D, n = threadIdx.x;
+  const long long g = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long nseg = (ntiles + seg_len - 1) / seg_len;
+  if (n >= M || g >= nseg) return;
+  const long long t0 = g * seg_len;
+  const long long t1 = t0 + seg_len < ntiles ? t0 + seg_len : ntiles;
+  const double* src = tile_buf + (size_t)blockIdx.y * ntiles * M * W;
+  double* dst = tile_start + (size_t)blockIdx.y * ntiles * M * SW;
+  const double* start = seg_start + (((size_t)blockIdx.y * nseg + g) * M + n) * SW;
+  if (n < D) carry_seg_apply_thread<EZ>(src, start, dst, M, n, t0, t1);
+  else carry_seg_apply_thread<EG>(src, start, dst, M, n, t0, t1);
+}
+
 // The shard's single aggregate (composition of its tiles in processing order): what a GPU
 // contributes to the carry exchange when a signal is time-chunked over ranks.
-template <class Elem>
+template <class EZ, class EG>
 __global__ void __launch_bounds__(32)
 scan_total_kernel(const DevProblem* __restrict__ probs, ScanArgs a, const double* __restrict__ tile_buf,
                   double* __restrict__ total) {
-  using Map = typename Elem::Map;
-  constexpr int W = Elem::kMapDoubles;
-  const int n = threadIdx.x, M = probs[0].M;
+  constexpr int W = EZ::kMapDoubles;
+  const int n = threadIdx.x, M = probs[0].M, D = probs[0].D;
   if (n >= M) return;
   const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  Map acc, e;
-  Elem::load_map(acc, tile_buf + (size_t)n * W);
-  for (long long t = 1; t < ntiles; ++t) {
-    Elem::load_map(e, tile_buf + ((size_t)t * M + n) * W);
-    Elem::compose(acc, e);
+  if (n < D) carry_seg_reduce_thread<EZ>(tile_buf, total + (size_t)n * W, M, n, 0, ntiles);
+  else carry_seg_reduce_thread<EG>(tile_buf, total + (size_t)n * W, M, n, 0, ntiles);
+}
+
+template <class Elem>
+__device__ __forceinline__ void scan_apply_entry_thread(const double* tile_slot, const double* s_map, double* s_state, int n, int M,
+                                                        int cnt) {
+  using Map = typename Elem::Map;
+  using State = typename Elem::State;
+  constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
+  State s;
+  Elem::load_state(s, tile_slot);
+  for (int j = 0; j < cnt; ++j) {
+    Map e;
+    Elem::load_map(e, s_map + ((size_t)j * M + n) * W);
+    Elem::store_state(s, s_state + ((size_t)j * M + n) * SW);
+    Elem::apply(e, s);
   }
-  Elem::store_map(acc, total + (size_t)n * W);
+}
+
+template <class Elem>
+__device__ __forceinline__ void scan_apply_thread(const DevProblem& P, const DevState& St, const ScanArgs& a, int n, long long chunk,
+                                                  const double* state_slot) {
+  using State = typename Elem::State;
+  Elem el(P, St, n, a);
+  el.begin_apply();
+  State s;
+  Elem::load_state(s, state_slot);
+  const long long s0 = chunk * kScanSteps;
+  const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
+  scan_walk(el, a, s0, s1, [&](long long k, const typename Elem::In& in, const typename Elem::Tab& tb) { el.step(k, in, tb, s); });
+  el.finish_apply();
 }
 
 template <class Elem>
 __global__ void __launch_bounds__(ScanBounds<Elem>::kThreads, ScanBounds<Elem>::kMinBlocks)
 scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
-                                  ScanArgs a, const double* __restrict__ chunk_buf,
-                                  const double* __restrict__ tile_start) {
-  using Map = typename Elem::Map;
-  using State = typename Elem::State;
+                  ScanArgs a, const double* __restrict__ chunk_buf,
+                  const double* __restrict__ tile_start, int n0, int cnt_lat) {
   constexpr int W = Elem::kMapDoubles, SW = Elem::kStateDoubles;
   const DevProblem& P = probs[blockIdx.y];
   const DevState& St = states[blockIdx.y];
-  const int n = threadIdx.x, c = threadIdx.y, M = P.M, CH = a.CH;
-  extern __shared__ double sm[];                 // [CH][M][SW] states entering each chunk | [CH][M][W] chunk maps
+  const int M = P.M, CH = a.CH;
+  const ScanThread th(threadIdx.x, n0, cnt_lat, CH);
+  const int n = th.n, c = th.c;
+  extern __shared__ double sm[];                 // [CH][cnt_lat][SW] states entering each chunk | [CH][cnt_lat][W] chunk maps
   const long long nchunks = scan_num_chunks(a.nsteps);
   const long long ntiles = scan_num_tiles(a.nsteps, CH);
   const long long first = (long long)blockIdx.x * CH;
   const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
   double* s_state = sm;
-  double* s_map = sm + (size_t)CH * M * SW;
+  double* s_map = sm + (size_t)CH * cnt_lat * SW;
   {
-    // stage this tile's chunk aggregates (contiguous in HBM) so the walk below runs from shared memory
-    const double* src = chunk_buf + ((size_t)blockIdx.y * nchunks + first) * M * W;
-    const int nthreads = blockDim.x * blockDim.y, tid = c * blockDim.x + n;
-    for (int i = tid; i < cnt * M * W; i += nthreads) s_map[i] = src[i];
-  }
-  __syncthreads();
-  if (c == 0 && n < M) {
-    State s;
-    Elem::load_state(s, tile_start + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * SW);
-    for (int j = 0; j < cnt; ++j) {
-      Map e;
-      Elem::load_map(e, s_map + ((size_t)j * M + n) * W);
-      Elem::store_state(s, s_state + ((size_t)j * M + n) * SW);
-      Elem::apply(e, s);
+    // stage this family's share of the tile's chunk aggregates (cnt_lat * W contiguous doubles per chunk)
+    const double* src = chunk_buf + (((size_t)blockIdx.y * nchunks + first) * M + n0) * W;
+    const int row = cnt_lat * W;
+    for (int i = threadIdx.x; i < cnt * row; i += blockDim.x) {
+      const int j = i / row;
+      s_map[i] = src[(size_t)j * M * W + (i - j * row)];
     }
   }
   __syncthreads();
+  if (th.live && c == 0)
+    scan_apply_entry_thread<Elem>(tile_start + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * SW, s_map, s_state, n - n0,
+                                  cnt_lat, cnt);
+  __syncthreads();
   const long long chunk = first + c;
-  if (n >= M || chunk >= nchunks) return;
-  Elem el(P, St, n, a);
-  el.begin_apply();
-  State s;
-  Elem::load_state(s, s_state + ((size_t)c * M + n) * SW);
-  const long long s0 = chunk * kScanSteps;
-  const long long s1 = (s0 + kScanSteps < a.nsteps) ? s0 + kScanSteps : a.nsteps;
-  scan_walk(el, a, s0, s1, [&](long long k, const typename Elem::In& in, const typename Elem::Tab& tb) { el.step(k, in, tb, s); });
-  el.finish_apply();
+  if (!th.live || chunk >= nchunks) return;
+  scan_apply_thread<Elem>(P, St, a, n, chunk, s_state + ((size_t)c * cnt_lat + (n - n0)) * SW);
 }
 
 }  // namespace nsagp
