@@ -405,9 +405,9 @@ def run_gpu(args):
         for name, fn in (("c3_one_signal_500k", lambda: bw.one_signal_chunked(ctx, "full", 500000, 20, 7, label="C3")),
                          ("ihgp_one_signal_10M", lambda: bw.one_signal_chunked(ctx, "ihgp", args.long_T, 20, 9, reps=1, warm=1,
                                                                                exact=(world == 1), burnin=100000,
-                                                                               label="north_star 10M")),
+                                                                               label="north_star 10M", ep_itts_1=True)),
                          ("c5_batch_256_clips", lambda: bw.c5_batch(ctx)),
-                         ("c4_giekf", lambda: bw.c4_giekf(ctx))):
+                         ("c4_giekf", lambda: bw.c4_giekf(ctx, cpu_baseline=(world == 1)))):
             try:
                 extras[name] = fn()
             except Exception as e:                       # an extra workload must never take the headline line down

@@ -83,7 +83,8 @@ def _timed_chunked(ctx, plan, dcomm, reps, warm):
     return t, ph
 
 
-def one_signal_chunked(ctx, kind, T, itts, seed, reps=2, warm=1, chunks_per_gpu=148, burnin=60000, exact=True, label=""):
+def one_signal_chunked(ctx, kind, T, itts, seed, reps=2, warm=1, chunks_per_gpu=148, burnin=60000, exact=True, label="",
+                       ep_itts_1=False):
     """ONE signal of T samples time-chunked over the ranks (strong scaling)."""
     nsagp, lm = ctx.nsagp, ctx.lm
     ihgp = kind == "ihgp"
@@ -120,6 +121,19 @@ def one_signal_chunked(ctx, kind, T, itts, seed, reps=2, warm=1, chunks_per_gpu=
         res["parallel_first_pass"]["nlZ_rel_dev_vs_exact"] = float(np.max(np.abs(nlz_par - nlz_exact) / np.abs(nlz_exact)))
         res["parallel_first_pass"]["speedup_vs_exact_same_gpus"] = res["exact"]["ms"] / ms
     plan.close()
+    if ep_itts_1:
+        # ONE sweep (ep_itts = 1: first filter pass + smoother), what the reference's training runs
+        # (experiments/train_model.m:59-60), on the same signal with the parallel first pass
+        plan1 = nsagp.Plan(lm.KIND_IHGP if ihgp else lm.KIND_FULL, [mdl], [(_mom(nsagp), np.log([hyp.w_lik]), hyp.W)], ALPHA, damp[:1], 1,
+                           y[None, :], lm.MODE_PREDICT, tables=[tabs] if ihgp else None)
+        plan1.set_adf_parallel(chunks_per_gpu, burnin)
+        ms1, ph1 = _timed_chunked(ctx, plan1, dcomm, reps, warm)
+        mis1, scale1 = ctx.max_over_ranks(plan1.adf_mismatch())
+        res["ep_itts_1_parallel_first_pass"] = {"ms": ms1, "steps_per_s": T / ms1 * 1e3, "phases_ms": ph1,
+                                                "boundary_mismatch_rel": mis1 / scale1 if scale1 > 0 else None}
+        if exact:
+            res["ep_itts_1_exact_first_pass_steps_per_s"] = T / (res["exact"]["phases_ms"]["adf"] + ph1["smoother"]) * 1e3
+        plan1.close()
     dcomm.close()
     return res
 
@@ -172,7 +186,7 @@ def c5_batch(ctx, reps=2, warm=1, B=256, T=39062, n_clips=32):
     return out
 
 
-def c4_giekf(ctx, T=100000, reps=2):
+def c4_giekf(ctx, T=100000, reps=2, cpu_baseline=True):
     """gf_giekf_modulator_nmf predict, D=32 exp subbands x N=3 matern52 modulators (dense n = 73), six gaps per 20k
     samples, g_iter = 1, through the host-buffer C entry point; one signal per GPU."""
     nsagp, lm, L = ctx.nsagp, ctx.lm, ctx.L
@@ -211,7 +225,20 @@ def c4_giekf(ctx, T=100000, reps=2):
             best, wall = ms.copy(), w
     f_ms, s_ms, wall = ctx.max_over_ranks([best[0], best[1], wall])
     sm_hz = 1.965e9
-    return {"workload": "C4: gf_giekf_modulator_nmf predict, D=32 x N=3 (dense n=%d), T=%d, g_iter=1, missing-data gaps, one signal per GPU" % (n, T),
+    cpu = None
+    if ctx.rank == 0 and cpu_baseline:
+        # the oracle (NumPy restatement of matlab/gf_giekf_modulator_nmf.m, dense n x n arithmetic as in the reference)
+        # on a bounded prefix: the checker timed as the CPU baseline, never the thing measured
+        from oracle import giekf as ogk, ssmodel as oss
+        Tc = 400
+        ss_ref = lambda x, p1, p2, k1, k2: oss.ss_modulators_nmf(p1, p2, k1, k2)
+        t = np.arange(1.0, Tc + 1.0)
+        t0 = time.perf_counter()
+        ogk.gf_giekf_modulator_nmf(hyp.pack_log(), t, y[:Tc], ss_ref, None, t, K1, K2, 1, Dk, Nk, 1, 1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": Tc / dt, "unit": "time-steps/s", "cores": 1, "kind": "port",
+               "sample": "oracle/giekf.py (NumPy, dense n=%d), first %d samples of the same signal, g_iter=1 (%.1f s)" % (n, Tc, dt)}
+    return {"cpu_baseline": cpu,"workload": "C4: gf_giekf_modulator_nmf predict, D=32 x N=3 (dense n=%d), T=%d, g_iter=1, missing-data gaps, one signal per GPU" % (n, T),
             "scaling": "weak", "filter_ms": f_ms, "smoother_ms": s_ms, "steps_per_s": ctx.world * T / (f_ms + s_ms) * 1e3,
             "e2e_steps_per_s": ctx.world * T / wall, "filter_cycles_per_step": f_ms * 1e-3 * sm_hz / T,
             "smoother_dense_equiv_tflops": 12.3 * n ** 3 * T / (s_ms * 1e-3) / 1e12,

@@ -290,6 +290,10 @@ int nsagp_plan_adf_mismatch(nsagp_plan* plan, double* out2);
  * and lik_quad = sum over observed steps of v^2 / (2 S) (:99); the caller adds the constant part (:80). */
 int nsagp_fastfb(int32_t n, const double* A, const double* AKHA, const double* Kg, const double* HA, double S,
                  const double* G, const double* y, int64_t T, double* MS, double* lik_quad);
+/* Tuning knob of the frozen-site scans (csrc/scan.cuh): signals of at least `family_min_steps` steps run the subband
+ * and the modulator latents as two launches per phase, each computing at its own block size (default 400 000; 0 =
+ * always, used by the parity tests).  Results agree to rounding either way. */
+int nsagp_scan_config(int64_t family_min_steps);
 /* Device time (ms, CUDA events on the launch stream) of the phases of the last
  * nsagp_plan_run: [0] total, [1] ADF filter pass, [2] fixed-site filter passes,
  * [3] smoother passes, [4] site-update passes.  Returns the number written. */

@@ -670,6 +670,13 @@ int nsagp_plan_keep_pf(nsagp_plan* pl, int keep) {
   return NSAGP_OK;
 }
 
+long long g_fam_min_steps = 400000;             // see DISPATCH_FAM below
+int nsagp_scan_config(int64_t family_min_steps) {
+  if (family_min_steps < 0) return fail(NSAGP_ERR_INVALID, "family_min_steps must be >= 0");
+  g_fam_min_steps = family_min_steps;
+  return NSAGP_OK;
+}
+
 int nsagp_release_cache(void) {
   g_cache.clear();
   return NSAGP_OK;
@@ -902,9 +909,12 @@ template <class EZ_, class EG_> struct ElemPair { using EZ = EZ_; using EG = EG_
 
 // Specialised pairs for the block-size combinations of the reference's kernels that matter (exp / matern32 / matern52
 // subbands with matern52 modulators); everything else computes both families at the padded size.
+// (On short signals -- below g_fam_min_steps steps -- the second launch per phase and the small modulator-family CTAs cost
+// more than the subband family saves: C2 at T = 1e5 was 2 ms slower per EP run; there both families run padded.)
 #define DISPATCH_FAM(PL, ELEMT, ...)                                                                           \
   do {                                                                                                         \
-    const int bm_ = (PL)->BM, bz_ = (PL)->bz, bg_ = (PL)->bg;                                                  \
+    const bool fam_ = (PL)->T >= g_fam_min_steps;                                                              \
+    const int bm_ = (PL)->BM, bz_ = fam_ ? (PL)->bz : -1, bg_ = (PL)->bg;                                      \
     if (bm_ == 3 && bz_ == 2 && bg_ == 3) { using Pair_ = ElemPair<ELEMT<3, 2>, ELEMT<3, 3>>; __VA_ARGS__; }    \
     else if (bm_ == 4 && bz_ == 4 && bg_ == 3) { using Pair_ = ElemPair<ELEMT<4, 4>, ELEMT<4, 3>>; __VA_ARGS__; } \
     else if (bm_ == 6 && bz_ == 6 && bg_ == 3) { using Pair_ = ElemPair<ELEMT<6, 6>, ELEMT<6, 3>>; __VA_ARGS__; } \
@@ -963,7 +973,7 @@ int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
     if ((rcl = launch(scan_reduce_kernel<typename Pair::EZ>, 0, pl->D)) || (rcl = launch(scan_reduce_kernel<typename Pair::EG>, pl->D, pl->N))) return rcl;
   }
   if (agg_host) {
-    scan_total_kernel<typename Pair::EZ, typename Pair::EG><<<1, 32, 0, g_stream>>>(pl->d_probs, a, pl->d_tile, pl->d_total);
+    scan_total_kernel<typename Pair::EZ, typename Pair::EG><<<1, 32, 0, g_stream>>>(pl->d_probs, pl->d_tile, ntiles, pl->d_total);
     LAUNCH_CHECK();
     CU(cudaMemcpyAsync(agg_host, pl->d_total, (size_t)pl->M * Pair::EZ::kMapDoubles * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));

@@ -285,14 +285,13 @@ __global__ void carry_seg_apply_kernel(const DevProblem* __restrict__ probs, con
 // contributes to the carry exchange when a signal is time-chunked over ranks.
 template <class EZ, class EG>
 __global__ void __launch_bounds__(32)
-scan_total_kernel(const DevProblem* __restrict__ probs, ScanArgs a, const double* __restrict__ tile_buf,
+scan_total_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ maps, long long nmaps,
                   double* __restrict__ total) {
   constexpr int W = EZ::kMapDoubles;
   const int n = threadIdx.x, M = probs[0].M, D = probs[0].D;
   if (n >= M) return;
-  const long long ntiles = scan_num_tiles(a.nsteps, a.CH);
-  if (n < D) carry_seg_reduce_thread<EZ>(tile_buf, total + (size_t)n * W, M, n, 0, ntiles);
-  else carry_seg_reduce_thread<EG>(tile_buf, total + (size_t)n * W, M, n, 0, ntiles);
+  if (n < D) carry_seg_reduce_thread<EZ>(maps, total + (size_t)n * W, M, n, 0, nmaps);
+  else carry_seg_reduce_thread<EG>(maps, total + (size_t)n * W, M, n, 0, nmaps);
 }
 
 template <class Elem>

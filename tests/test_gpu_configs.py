@@ -254,3 +254,37 @@ def test_c2_bench_schedule_prefix_against_oracle(nsagp, gpu_lib):
     r = bench.prefix_check(nsagp, seed=2026, Tp=2000, itts=20)
     assert r["lZ_rel_err"] < TOL_SCAN and r["Eft_rel_err"] < TOL_SCAN and r["ttau_rel_err"] < TOL_SCAN
     assert r["lZ_rel_err_first_sweep"] < TOL_SEQ
+
+
+# ------------------------------------------------------------------------------------------ family-specialised scans
+@pytest.fixture
+def family_scans(nsagp):
+    """Force the per-family form of the frozen-site scans (default: only signals of >= 400 000 steps)."""
+    L = nsagp._lib
+    L.check(L.lib().nsagp_scan_config(0))
+    yield
+    L.check(L.lib().nsagp_scan_config(400000))
+
+
+@pytest.mark.parametrize("D,N,k1,k2", [(16, 3, "exp", "matern52"),        # (BM, bz, bg) = (3, 2, 3): C2 / C3
+                                        (5, 2, "matern32", "matern52"),    # (4, 4, 3): the demo's kernels
+                                        (4, 2, "matern52", "matern52"),    # (6, 6, 3)
+                                        (4, 2, "exp", "exp")])             # no specialised pair: padded path
+@pytest.mark.parametrize("entry_name", ["ihgp", "gfep"])
+def test_family_specialised_scans_match_oracle(nsagp, gpu_lib, family_scans, entry_name, D, N, k1, k2):
+    """Subband and modulator latents as separate launches, each at its own block size (csrc/scan.cuh), against the
+    oracle: predict mode, 3 EP iterations, gaps."""
+    from oracle import gf_ep, ihgp_ep
+    T = 330
+    pb = make_problem(nsagp, D, N, T, k1, k2, seed=90 + D, kind="precalc", p=9, shift=1.0, gaps=True)
+    damping = np.linspace(0.4, 0.2, 3)
+    if entry_name == "ihgp":
+        ref, got = ihgp_ep.ihgp_ep_modulator_nmf, nsagp.ihgp_ep_modulator_nmf
+    else:
+        ref, got = gf_ep.gf_ep_modulator_nmf, nsagp.gf_ep_modulator_nmf
+    Eo, Vo, _, _, _, oo = ref(*_args(pb, "ref", pb["t"], 0.75, damping, 3))
+    Eg, Vg, _, _, _, og = got(*_args(pb, "gpu", pb["t"], 0.75, damping, 3))
+    assert rel_err(Eg, Eo) < TOL_SCAN and rel_err(Vg, Vo) < TOL_SCAN
+    assert rel_err(og["nlZ"], oo["nlZ"]) < TOL_SCAN and rel_err(og["MS"], oo["MS"]) < TOL_SCAN
+    assert rel_err(og["ttau"], oo["ttau"]) < TOL_SCAN and rel_err(og["MF"], oo["MF"]) < TOL_SCAN
+    assert og["n_negcav"] == oo["n_negcav"]
