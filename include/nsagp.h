@@ -191,6 +191,20 @@ int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_
 int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                       const double* y, int64_t T, int32_t mode, nsagp_outputs* out);
 
+/* gf_giekf_modulator_nmf with GradObj = 'on' and no test inputs (gf_giekf_modulator_nmf.m:296-437): the EKF energy
+ * and its gradient by the sensitivity equations, one (dm_j, dP_j) recursion per hyper-parameter j.
+ * model: A = expm(F), Q = Pinf - A Pinf A' (:355-357).  Every parameter lives in ONE latent (ss_modulators_nmf.m:25-129)
+ * or in none (the noise variance, j = 0 in the reference): latent[j] in -1 .. D+N-1, and for that latent's block
+ *   dA[j]    = lower-left block of expm([F 0; dF_j F])       (:328-338)
+ *   dQ[j]    = dPinf_j - dA Pinf A' - A dPinf_j A' - (dA Pinf A')'   (:362-364)
+ *   dPinf[j] = the initial dP_j                               (:314)
+ * each a bmax-by-bmax column-major block, bmax = max(bz, bg), zero padded; dR[j] = d sigma2 / d theta_j (:96).
+ * Out: edata[1], gdata[nparam] BEFORE the log-scale factor exp(w) of :432-433.  NaN + NSAGP_ERR_NAN as nsagp_giekf.
+ * One CTA per parameter, P and dP_j in shared memory: needs 2 n^2 doubles <= ~220 KB (n <= ~115). */
+int nsagp_giekf_grad(const nsagp_model* model, const double* W, double sigma2, int32_t nparam, const int32_t* latent,
+                     const double* dA, const double* dQ, const double* dPinf, const double* dR, const double* y, int64_t T,
+                     double* edata, double* gdata);
+
 /* Form of the dense RTS pass of nsagp_giekf (gf_giekf_modulator_nmf_constraints.m:221-253):
  * smoother_form 0 = automatic (the parallel scan over time on the FP64 tensor cores when n <= 80, csrc/ekfscan.cuh),
  * 1 = the first-generation kernels (filter and a smoother that is sequential in time; kept as a cross-check),

@@ -12,6 +12,7 @@
 //   out = nsagp_mex('ep_full', model, lik, ep, [],     yall, mode)
 //   out = nsagp_mex('giekf', model, W, sigma2, g_iter, l_iter, yall, mode)        (P reset every global iteration)
 //   out = nsagp_mex('giekf_carry', model, W, sigma2, g_iter, l_iter, yall, mode)  (gf_giekf_modulator_nmf.m: m, P carried)
+//   [edata, gdata] = nsagp_mex('giekf_grad', model, W, sigma2, latent, dA, dQ, dPinf, dR, yall)   (:296-437, GradObj 'on')
 //   [Esig, Vsig, Eft_mod, Varft_mod] = nsagp_mex('mc_reconstruct', Eft, Varft, W, link_shift, sqrt_model, s, Z_or_seed)
 //   [lZ, dlZ, d2lZ] = nsagp_mex('mom', lik, D, N, ep_fraction, y, mu, s2)
 //   [MS, lik_quad] = nsagp_mex('fastfb', A, AKHA, K, HA, S, G_or_empty, y)
@@ -169,6 +170,32 @@ void giekf_call(bool carry, int nlhs, mxArray* plhs[], int nrhs, const mxArray* 
   plhs[0] = s;
 }
 
+// [edata, gdata] = nsagp_mex('giekf_grad', model, W, sigma2, latent, dA, dQ, dPinf, dR, yall): latent nparam-by-1
+// (0-based, -1 = none), dA / dQ / dPinf bmax-by-bmax-by-nparam (include/nsagp.h nsagp_giekf_grad).
+void giekf_grad_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs != 10) mexErrMsgIdAndTxt("nsagp:arg", "usage: [edata, gdata] = nsagp_mex('giekf_grad', model, W, sigma2, latent, dA, dQ, dPinf, dR, yall)");
+  nsagp_model model;
+  fill_model(prhs[1], &model);
+  need(prhs[2], (size_t)model.D * model.N, "W");
+  const double* W = dbl(prhs[2], "W");
+  const double sigma2 = mxGetScalar(prhs[3]);
+  const size_t nparam = mxGetNumberOfElements(prhs[4]);
+  const size_t bmax = (size_t)(model.bz > model.bg ? model.bz : model.bg);
+  const double* latd = dbl(prhs[4], "latent");
+  std::vector<int32_t> latent(nparam);
+  for (size_t j = 0; j < nparam; ++j) latent[j] = (int32_t)latd[j];
+  need(prhs[5], nparam * bmax * bmax, "dA"); need(prhs[6], nparam * bmax * bmax, "dQ"); need(prhs[7], nparam * bmax * bmax, "dPinf");
+  need(prhs[8], nparam, "dR");
+  const double* y = dbl(prhs[9], "yall");
+  const int64_t T = (int64_t)mxGetNumberOfElements(prhs[9]);
+  plhs[0] = mxCreateDoubleMatrix(1, 1, mxREAL);
+  mxArray* g = mxCreateDoubleMatrix(1, (mwSize)nparam, mxREAL);
+  const int st = nsagp_giekf_grad(&model, W, sigma2, (int32_t)nparam, latent.data(), dbl(prhs[5], "dA"), dbl(prhs[6], "dQ"),
+                                  dbl(prhs[7], "dPinf"), dbl(prhs[8], "dR"), y, T, mxGetDoubles(plhs[0]), mxGetDoubles(g));
+  if (st != NSAGP_ERR_NAN) check(st);            // NaN energy and gradient are values the reference returns (:391-394)
+  if (nlhs > 1) plhs[1] = g; else mxDestroyArray(g);
+}
+
 // [Esig, Vsig, Eft_mod, Varft_mod] = nsagp_mex('mc_reconstruct', Eft, Varft, W, link_shift, sqrt_model, s, Z_or_seed)
 // Z_or_seed: a T-by-s-by-M array of standard-normal draws (page i = latent i), or a scalar seed.
 void mc_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
@@ -239,6 +266,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   else if (c == "ep_full") ep_call(false, nlhs, plhs, nrhs, prhs);
   else if (c == "giekf") giekf_call(false, nlhs, plhs, nrhs, prhs);
   else if (c == "giekf_carry") giekf_call(true, nlhs, plhs, nrhs, prhs);
+  else if (c == "giekf_grad") giekf_grad_call(nlhs, plhs, nrhs, prhs);
   else if (c == "mc_reconstruct") mc_call(nlhs, plhs, nrhs, prhs);
   else if (c == "mom") mom_call(nlhs, plhs, nrhs, prhs);
   else if (c == "fastfb") fastfb_call(nlhs, plhs, nrhs, prhs);

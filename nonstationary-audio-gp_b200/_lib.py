@@ -23,7 +23,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("NSAGP_LIB") or os.path.join(CSRC, "libnsagp.so")
 _SOURCES = ["api.cu", "api_full.inc", "common.cuh", "mom.cuh", "momcta.cuh", "mombatch.cuh", "lookup.cuh", "ihgp.cuh",
             "gfep.cuh", "adfcta.cuh", "fastmath.cuh", "scan.cuh", "ekf.cuh", "ekfscan.cuh", "mcrec.cuh", "api_mc.inc", "api_ekf.inc", "api_chunk.inc", "api_tables.inc", "comm.cuh",
-            "api_comm.inc", "siteupd.cuh", "ekfbig.cuh", "fastfb.cuh", "api_fb.inc"]
+            "api_comm.inc", "siteupd.cuh", "ekfbig.cuh", "fastfb.cuh", "api_fb.inc", "ekfgrad.cuh"]
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -126,6 +126,8 @@ def lib():
     L.nsagp_mc_reconstruct.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_double,
                                        C.c_int32, c_double_p, C.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p]
     L.nsagp_giekf_carry.argtypes = L.nsagp_giekf.argtypes
+    L.nsagp_giekf_grad.argtypes = [C.POINTER(Model), c_double_p, C.c_double, C.c_int32, C.POINTER(C.c_int32), c_double_p,
+                                   c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]
     L.nsagp_giekf_config.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.nsagp_giekf_timings.argtypes = [c_double_p, C.c_int32]
     L.nsagp_plan_set_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
@@ -156,7 +158,7 @@ EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_s
            "nsagp_plan_set_adf_form", "nsagp_fastmath_eval", "nsagp_release_cache", "nsagp_giekf", "nsagp_plan_set_range",
            "nsagp_plan_stage", "nsagp_ihgp_tables", "nsagp_giekf_config", "nsagp_giekf_timings", "nsagp_giekf_carry", "nsagp_mc_reconstruct",
            "nsagp_comm_create", "nsagp_comm_export", "nsagp_comm_connect", "nsagp_comm_destroy", "nsagp_plan_comm_slot_doubles",
-           "nsagp_plan_run_chunked", "nsagp_plan_set_adf_parallel", "nsagp_plan_adf_mismatch", "nsagp_fastfb", "nsagp_scan_config"]
+           "nsagp_plan_run_chunked", "nsagp_plan_set_adf_parallel", "nsagp_plan_adf_mismatch", "nsagp_fastfb", "nsagp_scan_config", "nsagp_giekf_grad"]
 
 
 def check(status):

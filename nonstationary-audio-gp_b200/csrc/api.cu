@@ -23,6 +23,7 @@
 #include "ekf.cuh"
 #include "ekfscan.cuh"
 #include "ekfbig.cuh"
+#include "ekfgrad.cuh"
 #include "mcrec.cuh"
 #include "comm.cuh"
 #include "siteupd.cuh"
@@ -1295,6 +1296,12 @@ int nsagp_giekf(const nsagp_model* model, const double* W, double sigma2, int32_
 int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, int32_t g_iter, int32_t l_iter,
                       const double* y, int64_t T, int32_t mode, nsagp_outputs* out) {
   return giekf_impl(model, W, sigma2, g_iter, l_iter, 1, y, T, mode, out);
+}
+
+int nsagp_giekf_grad(const nsagp_model* model, const double* W, double sigma2, int32_t nparam, const int32_t* latent,
+                     const double* dA, const double* dQ, const double* dPinf, const double* dR, const double* y, int64_t T,
+                     double* edata, double* gdata) {
+  return giekf_grad_impl(model, W, sigma2, nparam, latent, dA, dQ, dPinf, dR, y, T, edata, gdata);
 }
 
 int nsagp_mc_reconstruct(int32_t D, int32_t N, int64_t T, int32_t s, const double* Eft, const double* Varft, const double* W,

@@ -322,10 +322,17 @@ def ihgp_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, nu
 
 
 def gf_giekf_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter,
-                           nargout=6, debug_cov=False):
-    """Drop-in for matlab/gf_giekf_modulator_nmf.m (GradObj = 'off'): log-scale parameter vector
+                           GradObj="off", nargout=6, debug_cov=False, balance_derivatives=False):
+    """Drop-in for matlab/gf_giekf_modulator_nmf.m: log-scale parameter vector
     (:70-73), balanced model (:78-85), and the state (m, P) initialised on the first global iteration
-    only (:127-131) -- the smoothed mean and covariance of step 1 start the next filter pass."""
+    only (:127-131) -- the smoothed mean and covariance of step 1 start the next filter pass.
+
+    ``GradObj='on'`` with ``xt`` empty returns ``(energy, gradient)`` with the analytic gradient of :296-437 over
+    ``w(1:end-D*N)`` (the sensitivity equations; csrc/ekfgrad.cuh).  The reference balances F, L, H, Pinf but leaves
+    dF and dPinf in the unbalanced coordinates (its balancing loop is commented out, :82-84), so its gradient is the
+    derivative of the energy only where balancing is the identity; ``balance_derivatives=True`` runs that loop."""
+    if GradObj != "off" and not (xt is not None and np.size(xt) > 0):
+        return _giekf_grad(w, x, y, ss, kernel1, kernel2, num_lik_params, D, N, balance_derivatives)
     return _giekf(w, x, y, ss, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, None, nargout, debug_cov)
 
 
@@ -338,6 +345,91 @@ def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, n
     (its measurement model is hard-wired, :133-138)."""
     return _giekf(w, x, y, ss, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter,
                   (constraints, w_fixed, tune_hypers), nargout, debug_cov)
+
+
+def _deriv_blocks(stack, starts, sizes):
+    """[(latent, block)] of a derivative stack: a ssmodel.DerivStack as it is, a dense n x n x P array (what a
+    reference-style ``ss`` closure returns) by locating the one diagonal block each slice occupies."""
+    if isinstance(stack, ssmodel.DerivStack):
+        return stack.items
+    if stack is None:
+        raise ValueError("GradObj='on' needs the derivative stacks dF, dQc, dPinf from the ss closure (outputs 6-8)")
+    stack = np.asarray(stack, float)
+    items = []
+    for p in range(stack.shape[2]):
+        X = stack[:, :, p]
+        rows = np.flatnonzero(np.any(X != 0, axis=1) | np.any(X != 0, axis=0))
+        lat = int(np.searchsorted(starts, rows[0], side="right") - 1) if rows.size else 0
+        o, b = starts[lat], sizes[lat]
+        if rows.size and (rows[0] < o or rows[-1] >= o + b):
+            raise ValueError("derivative slice %d is not confined to one latent's block" % p)
+        items.append((lat, X[o:o + b, o:o + b].copy()))
+    return items
+
+
+def _giekf_grad(w, x, y, ss, kernel1, kernel2, num_lik_params, D, N, balance_derivatives):
+    """Host side of gf_giekf_modulator_nmf.m:296-437: per-parameter blocks of dA, dQ, dPinf (:328-338, :362-364),
+    then nsagp_giekf_grad."""
+    import scipy.linalg as sla
+    yall, _ = merge_inputs(x, y, None)
+    w = np.asarray(w, float).ravel()
+    lik_param, param1, param2, Wnmf = _unpack_log(w, num_lik_params, D, N)
+    res = ss(x, param1, param2, kernel1, kernel2)
+    F, L, Qc, H, Pinf = res[:5]
+    Fb, Lb, Hb, Pb, Tm = ssmodel.balance(F, L, H, Pinf, return_T=True)              # :78-81
+    sigma2 = float(np.exp(np.asarray(lik_param, float).ravel()[0]))
+    A = sla.expm(Fb)                                                                 # :355-357
+    Q = Pb - A @ Pb @ A.T
+    mdl = ssmodel.to_block_model(A, Q, Hb, Pb, D, N)
+    st, sizes = mdl.starts(), mdl.block_sizes()
+    dFi = _deriv_blocks(res[5] if len(res) > 5 else None, st, sizes)
+    dPi = _deriv_blocks(res[7] if len(res) > 7 else None, st, sizes)
+    nparam = 1 + len(dFi)                                                            # the noise variance first (:93-96)
+    if nparam != w.size - D * N:
+        raise ValueError("ss returned %d derivative slices, w(1:end-D*N) has %d entries" % (len(dFi), w.size - D * N))
+    bmax = max(mdl.bz, mdl.bg)
+    latent = np.full(nparam, -1, np.int32)
+    dA = np.zeros((nparam, bmax, bmax)); dQ = np.zeros_like(dA); dP0 = np.zeros_like(dA)
+    dR = np.zeros(nparam); dR[0] = 1.0
+    for j, ((lat, dFj), (lat2, dPj)) in enumerate(zip(dFi, dPi), start=1):
+        if lat != lat2 and np.any(dPj != 0) and np.any(dFj != 0):
+            raise ValueError("dF and dPinf of parameter %d live in different latents" % j)
+        if not np.any(dFj != 0) and np.any(dPj != 0):
+            lat = lat2
+        o, b = st[lat], sizes[lat]
+        sl = slice(o, o + b)
+        if not np.any(dFj != 0):
+            dFj = np.zeros((b, b))                                                   # e.g. a variance: F does not depend on it
+        if not np.any(dPj != 0):
+            dPj = np.zeros((b, b))                                                   # e.g. a frequency: Pinf does not depend on it
+        if balance_derivatives:                                                      # the commented-out loop, :82-84
+            Tl = Tm[sl, sl]
+            dFj = sla.solve(Tl, dFj @ Tl)
+            dPj = sla.solve(Tl, sla.solve(Tl, dPj).T).T
+        Fl, Pl = Fb[sl, sl], Pb[sl, sl]
+        AA = sla.expm(np.block([[Fl, np.zeros((b, b))], [dFj, Fl]]))                 # :328-338, one latent's block
+        Al, dAl = AA[:b, :b], AA[b:, :b]
+        dAPAt = dAl @ Pl @ Al.T
+        latent[j] = lat
+        dA[j, :b, :b] = dAl
+        dQ[j, :b, :b] = dPj - dAPAt - Al @ dPj @ Al.T - dAPAt.T                      # :362-364
+        dP0[j, :b, :b] = dPj
+    arrs = [_lib.as_f64(a) for a in (mdl.A, mdl.Q, mdl.Pinf, mdl.h)]
+    cm = _lib.Model()
+    cm.D, cm.N, cm.bz, cm.bg = mdl.D, mdl.N, mdl.bz, mdl.bg
+    cm.A, cm.Q, cm.Pinf, cm.h = [_lib.dptr(a) for a in arrs]
+    Wf = np.asfortranarray(np.asarray(Wnmf, float))
+    # blocks column-major with leading dimension bmax
+    pack = lambda X: _lib.as_f64(np.ascontiguousarray(np.transpose(X, (0, 2, 1))).ravel())
+    bA, bQ, bP, vR, yb = pack(dA), pack(dQ), pack(dP0), _lib.as_f64(dR), _lib.as_f64(yall)
+    edata = np.zeros(1); gdata = np.zeros(nparam)
+    status = _lib.lib().nsagp_giekf_grad(C.byref(cm), Wf.ctypes.data_as(_lib.c_double_p), sigma2, nparam,
+                                         latent.ctypes.data_as(C.POINTER(C.c_int32)), _lib.dptr(bA), _lib.dptr(bQ), _lib.dptr(bP),
+                                         _lib.dptr(vR), _lib.dptr(yb), yall.size, _lib.dptr(edata), _lib.dptr(gdata))
+    if status == -5:                                                    # NSAGP_ERR_NAN: the reference returns NaNs (:391-394)
+        return float("nan"), np.full(nparam, np.nan)
+    _lib.check(status)
+    return float(edata[0]), gdata * np.exp(w[:nparam])                  # :431-433
 
 
 def _giekf(w, x, y, ss, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, constrained, nargout, debug_cov):

@@ -63,12 +63,56 @@ def kernel_sde(kernel, magnSigma2, lengthScale):
     return F, L, np.array([[Qc]]), H, Pinf
 
 
+def kernel_sde_derivs(kernel, magnSigma2, lengthScale):
+    """Derivatives of ``kernel_sde`` with respect to (magnSigma2, lengthScale): three arrays with a trailing axis
+    of length 2 (dF, dQc, dPinf), the values of cf_*_to_ss.m's 6th-8th outputs.  With lam = c / ell every entry is
+    a monomial in ell -- F[last, i] ~ ell^-(tau-i), Pinf[i, j] ~ s2 ell^-(i+j), Qc ~ s2 ell^-(2 tau - 1) -- so the
+    derivatives are the entries times (-power / ell) and (1 / s2)."""
+    s2, ell = float(magnSigma2), float(lengthScale)
+    F, _, Qc, _, Pinf = kernel_sde(kernel, s2, ell)
+    tau = F.shape[0]
+    dF = np.zeros((tau, tau, 2)); dQc = np.zeros((1, 1, 2)); dPinf = np.zeros((tau, tau, 2))
+    for i in range(tau):
+        dF[tau - 1, i, 1] = -(tau - i) * F[tau - 1, i] / ell
+    dQc[0, 0, 0] = Qc[0, 0] / s2
+    dQc[0, 0, 1] = -(2 * tau - 1) * Qc[0, 0] / ell
+    dPinf[:, :, 0] = Pinf / s2
+    ij = np.add.outer(np.arange(tau), np.arange(tau))
+    dPinf[:, :, 1] = -ij * Pinf / ell
+    return dF, dQc, dPinf
+
+
+class DerivStack:
+    """One of the derivative stacks dF / dQc / dPinf of ``ss_modulators_nmf`` (its 6th-8th outputs).  Every slice is
+    zero outside ONE latent's diagonal block (ss_modulators_nmf.m:25-129), so the stack is kept as
+    ``(latent, block)`` pairs; ``np.asarray(stack)`` gives the reference's dense n x n x (3D+2N) array."""
+
+    def __init__(self, n, starts, items):
+        self.n, self.starts, self.items = int(n), np.asarray(starts, int), list(items)
+
+    @property
+    def shape(self):
+        return (self.n, self.n, len(self.items))
+
+    def __len__(self):
+        return len(self.items)
+
+    def __array__(self, dtype=None, copy=None):
+        out = np.zeros(self.shape)
+        for p, (lat, blk) in enumerate(self.items):
+            o = self.starts[lat]
+            out[o:o + blk.shape[0], o:o + blk.shape[1], p] = blk
+        return out if dtype is None else out.astype(dtype)
+
+
 def ss_modulators_nmf(w_subband, w_modulator, kernel1, kernel2):
     """``[F,L,Qc,H,Pinf,dF,dQc,dPinf] = ss_modulators_nmf(...)``.
 
     D quasi-periodic subbands (kernel1 x cosine(omega), block 2*tau1) followed by
-    N modulators (kernel2, block tau3).  Derivative stacks are returned as None:
-    the EP entry points never read them (gf_ep_modulator_nmf.m:78)."""
+    N modulators (kernel2, block tau3).  The derivative stacks (slices ordered
+    [var1 (D), len1 (D), omega (D), var2 (N), len2 (N)], ss_modulators_nmf.m:76-78,127-129) come back as
+    ``DerivStack`` objects: only gf_giekf_modulator_nmf with GradObj = 'on' reads them
+    (the EP entry points discard them, gf_ep_modulator_nmf.m:78)."""
     ws = np.asarray(w_subband, float).ravel()
     wm = np.asarray(w_modulator, float).ravel()
     if ws.size % 3 or wm.size % 2:
@@ -89,8 +133,27 @@ def ss_modulators_nmf(w_subband, w_modulator, kernel1, kernel2):
     for j in range(N):
         F2, L2, Qc2, H2, P2 = kernel_sde(kernel2, wm[j], wm[N + j])
         Fs.append(F2); Ls.append(L2); Qs.append(Qc2); Hs.append(H2); Ps.append(P2)
-    return (sla.block_diag(*Fs), sla.block_diag(*Ls), sla.block_diag(*Qs),
-            sla.block_diag(*Hs), sla.block_diag(*Ps), None, None, None)
+    F = sla.block_diag(*Fs)
+    n = F.shape[0]
+    tau1, tau3 = kernel_order(kernel1), kernel_order(kernel2)
+    starts = np.concatenate([2 * tau1 * np.arange(D), 2 * tau1 * D + tau3 * np.arange(N)])
+    qstarts = np.concatenate([2 * np.arange(D), 2 * D + np.arange(N)])
+    dFs, dQs, dPs = [None] * (3 * D + 2 * N), [None] * (3 * D + 2 * N), [None] * (3 * D + 2 * N)
+    J2 = np.array([[0.0, -1.0], [1.0, 0.0]])
+    for d in range(D):
+        dF1, dQ1, dP1 = kernel_sde_derivs(kernel1, ws[d], ws[D + d])
+        for which, p in ((0, d), (1, D + d)):
+            dFs[p] = (d, np.kron(dF1[:, :, which], I2))
+            dQs[p] = (d, dQ1[0, 0, which] * I2)
+            dPs[p] = (d, np.kron(dP1[:, :, which], I2))
+        p = 2 * D + d                                                   # omega enters the rotation only
+        dFs[p] = (d, np.kron(np.eye(tau1), J2)); dQs[p] = (d, np.zeros((2, 2))); dPs[p] = (d, np.zeros((2 * tau1, 2 * tau1)))
+    for j in range(N):
+        dF2, dQ2, dP2 = kernel_sde_derivs(kernel2, wm[j], wm[N + j])
+        for which, p in ((0, 3 * D + j), (1, 3 * D + N + j)):
+            dFs[p] = (D + j, dF2[:, :, which]); dQs[p] = (D + j, dQ2[:, :, which]); dPs[p] = (D + j, dP2[:, :, which])
+    return (F, sla.block_diag(*Ls), sla.block_diag(*Qs), sla.block_diag(*Hs), sla.block_diag(*Ps),
+            DerivStack(n, starts, dFs), DerivStack(2 * D + N, qstarts, dQs), DerivStack(n, starts, dPs))
 
 
 def lti_disc(F, L=None, Qc=None, dt=1.0):
@@ -111,11 +174,12 @@ def lti_disc(F, L=None, Qc=None, dt=1.0):
     return A, Q
 
 
-def balance(F, L, H, Pinf):
+def balance(F, L, H, Pinf, return_T=False):
     """``[T,F]=balance(F); L=T\\L; H=H*T; LL=T\\chol(Pinf,'lower'); Pinf=LL*LL'``."""
     Fb, T = sla.matrix_balance(np.asarray(F, float), permute=True, scale=True, separate=False)
     LL = sla.solve(T, np.linalg.cholesky(Pinf))
-    return Fb, sla.solve(T, L), np.asarray(H, float) @ T, LL @ LL.T
+    res = (Fb, sla.solve(T, L), np.asarray(H, float) @ T, LL @ LL.T)
+    return res + (T,) if return_T else res
 
 
 @dataclasses.dataclass

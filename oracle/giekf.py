@@ -34,6 +34,19 @@ def funhd(x, H, D, N, W):
     return partials @ H
 
 
+def funhd2(x, H, D, N, W):
+    """gf_giekf_modulator_nmf.m:459-472 (n x n second derivative of h).  As in funhd above, the derivative with
+    respect to the latent values is chained through H instead of being scattered to the columns where
+    ``sum(H,1)==1`` (:452, :470): the two agree when the observed components of H are 1, and the scatter is
+    ill-defined once balancing has rescaled them."""
+    z = H[:D] @ x
+    g = H[D:D + N] @ x
+    dl = _dlinkf(g)
+    Wd = W * dl[None, :]
+    foo2 = np.block([[np.zeros((D, D)), Wd], [Wd.T, np.diag((z @ W) * dl * (1 - dl))]])
+    return H.T @ foo2 @ H
+
+
 def iekf_update1(M, P, y, D, N, H, Wnmf, R, iters):
     """iekf_update1.m:110-117 (V = I): relinearise at the *current* mean, no
     re-centering on the prior mean; covariance from the last linearisation."""
@@ -109,6 +122,58 @@ def giekf_energy(F, H, Pinf, sigma2, Wnmf, yall, D, N):
     return edata
 
 
+def giekf_energy_grad(F, H, Pinf, dF, dPinf, sigma2, Wnmf, yall, D, N):
+    """Energy and its sensitivity-equation gradient, gf_giekf_modulator_nmf.m:296-437 with GradObj = 'on'.
+    dF / dPinf: n x n x nparam with the zero slice of the noise parameter first (:93-96).  Returns
+    (edata, gdata) BEFORE the log-scale factor of :432-433."""
+    d = F.shape[0]
+    nparam = dF.shape[2]
+    Z = np.zeros((d, d))
+    m = np.zeros(d); P = Pinf.copy()
+    dm = np.zeros((d, nparam)); dP = dPinf.copy()
+    dR = np.zeros(nparam); dR[0] = 1.0
+    AA = [sla.expm(np.block([[F, Z], [dF[:, :, j], F]])) for j in range(nparam)]      # :328-338
+    edata = 0.0
+    gdata = np.zeros(nparam)
+    A = AA[0][:d, :d]
+    Q = Pinf - A @ Pinf @ A.T
+    for k in range(yall.size):
+        for j in range(nparam):                                        # :344-369
+            foo = AA[j] @ np.concatenate([m, dm[:, j]])
+            mm = foo[:d]
+            dm[:, j] = foo[d:]
+            if j == 0:
+                PP = A @ P @ A.T + Q
+            dA = AA[j][d:, :d]
+            dAPinfAt = dA @ Pinf @ A.T
+            dQ = dPinf[:, :, j] - dAPinfAt - A @ dPinf[:, :, j] @ A.T - dAPinfAt.T
+            dAPAt = dA @ P @ A.T
+            dP[:, :, j] = dAPAt + A @ dP[:, :, j] @ A.T + dAPAt.T + dQ
+        m = mm; P = PP                                                 # :372-373
+        mu = funh(m, H, D, N, Wnmf)
+        JH = funhd(m, H, D, N, Wnmf)
+        dJH = funhd2(m, H, D, N, Wnmf)
+        S = JH @ P @ JH + sigma2
+        if not S > 0:                                                  # :384-395
+            return math.nan, np.full(nparam, math.nan)
+        HtiS = JH / S
+        K = P @ HtiS
+        v = yall[k] - mu
+        vtiS = v / S
+        for j in range(nparam):                                        # :405-423
+            dmdJH = dm[:, j] @ dJH
+            dS = dmdJH @ P @ JH + JH @ dP[:, :, j] @ JH + JH @ P @ dmdJH + dR[j]
+            gdata[j] += 0.5 * dS / S - 0.5 * (JH @ dm[:, j]) * vtiS - 0.5 * vtiS * dS * vtiS - 0.5 * vtiS * (JH @ dm[:, j])
+            dK = dP[:, :, j] @ HtiS + P @ dmdJH / S - P @ HtiS * dS / S
+            dm[:, j] = dm[:, j] + dK * v - K * (JH @ dm[:, j])
+            dKSKt = np.outer(dK * S, K)
+            dP[:, :, j] = dP[:, :, j] - dKSKt - np.outer(K * dS, K) - dKSKt.T
+        edata += 0.5 * math.log(2 * math.pi) + math.log(math.sqrt(S)) + 0.5 * vtiS * v
+        m = m + K * v
+        P = P - np.outer(K * S, K)
+    return edata, gdata
+
+
 def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
                                        g_iter, l_iter, constraints, w_fixed, tune_hypers, want_cov=False):
     """gf_giekf_modulator_nmf_constraints.m:1 (``mom`` is ignored by the reference too)."""
@@ -126,13 +191,30 @@ def gf_giekf_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, n
     return giekf_energy(F, H, Pinf, sigma2, Wnmf, yall, D, N), np.zeros(np.size(w))
 
 
-def gf_giekf_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, want_cov=False):
-    """gf_giekf_modulator_nmf.m:1 (GradObj = 'off'): log-scale parameters (:70-73), balanced model (:78-85),
-    (m, P) carried across the global iterations (:127-131)."""
+def gf_giekf_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N, g_iter, l_iter, want_cov=False,
+                           GradObj="off", balance_derivatives=False):
+    """gf_giekf_modulator_nmf.m:1: log-scale parameters (:70-73), balanced model (:78-85), (m, P) carried across
+    the global iterations (:127-131).  GradObj = 'on' with xt empty: energy and analytic gradient (:296-437), where
+    the reference balances F, L, H, Pinf but NOT dF / dPinf (its balancing loop is commented out, :82-84);
+    ``balance_derivatives`` runs that loop (then the result is the derivative of the energy)."""
     yall, return_ind = merge_inputs(x, y, xt)
     lik_param, param1, param2, Wnmf = ssmodel.unpack_log(w, num_lik_params, D, N)
-    F, L, Qc, H, Pinf = ss(x, param1, param2, kernel1, kernel2)[:5]
-    F, L, H, Pinf, _ = ssmodel.balance_ss(F, L, H, Pinf)
+    res = ss(x, param1, param2, kernel1, kernel2)
+    F, L, Qc, H, Pinf = res[:5]
+    F, L, H, Pinf, Tb = ssmodel.balance_ss(F, L, H, Pinf)
+    if GradObj != "off" and not (xt is not None and np.size(xt) > 0):
+        dF, dPinf = np.asarray(res[5], float), np.asarray(res[7], float)
+        if balance_derivatives:                                       # the commented-out loop, :82-84
+            Ti = np.linalg.inv(Tb)
+            dF = np.stack([Ti @ dF[:, :, j] @ Tb for j in range(dF.shape[2])], axis=2)
+            dPinf = np.stack([Ti @ dPinf[:, :, j] @ Ti.T for j in range(dPinf.shape[2])], axis=2)
+        n = F.shape[0]
+        dF = np.concatenate([np.zeros((n, n, 1)), dF], axis=2)        # :93-96
+        dPinf = np.concatenate([np.zeros((n, n, 1)), dPinf], axis=2)
+        s2 = math.exp(float(np.asarray(lik_param).ravel()[0]))
+        edata, gdata = giekf_energy_grad(F, H, Pinf, dF, dPinf, s2, Wnmf, yall, D, N)
+        ww = np.asarray(w, float).ravel()[:np.size(w) - D * N]
+        return edata, gdata * np.exp(ww)                              # :432-433
     sigma2 = math.exp(float(np.asarray(lik_param).ravel()[0]))
     if xt is not None and np.size(xt) > 0:
         A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)

@@ -118,6 +118,79 @@ def ss_modulators_nmf(w_subband, w_modulator, kernel1, kernel2):
     return F, L, Qc, H, Pinf
 
 
+def _cf_derivs(kernel, magnSigma2, lengthScale):
+    """Derivative stacks (dF, dQc, dPinf), last axis = (magnSigma2, lengthScale), of one covariance function:
+    cf_exp_to_ss.m:70-92, cf_matern32_to_ss.m:78-104, cf_matern52_to_ss.m:82-112, cf_matern72_to_ss.m:84-116."""
+    s2, l = float(magnSigma2), float(lengthScale)
+    F, L, Qc, H, Pinf = _CF[kernel](s2, l)
+    t = F.shape[0]
+    dF = np.zeros((t, t, 2)); dQc = np.zeros((1, 1, 2)); dPinf = np.zeros((t, t, 2))
+    if kernel == "exp":
+        dF[0, 0, 1] = 1 / l ** 2
+        dQc[0, 0, 0] = 2 / l; dQc[0, 0, 1] = -2 * s2 / l ** 2
+        dPinf[0, 0, 0] = 1.0
+    elif kernel == "matern32":
+        dF[1, :, 1] = [6 / l ** 3, 2 * math.sqrt(3) / l ** 2]
+        dQc[0, 0, 0] = 12 * math.sqrt(3) / l ** 3; dQc[0, 0, 1] = -3 * 12 * math.sqrt(3) / l ** 4 * s2
+        dPinf[:, :, 0] = [[1, 0], [0, 3 / l ** 2]]
+        dPinf[:, :, 1] = [[0, 0], [0, -6 * s2 / l ** 3]]
+    elif kernel == "matern52":
+        dF[2, :, 1] = [15 * math.sqrt(5) / l ** 4, 30 / l ** 3, 3 * math.sqrt(5) / l ** 2]
+        dQc[0, 0, 0] = 400 * math.sqrt(5) / 3 / l ** 5; dQc[0, 0, 1] = -s2 * 2000 * math.sqrt(5) / 3 / l ** 6
+        kappa = 5 / 3 * s2 / l ** 2
+        k2 = -2 * kappa / l
+        dPinf[:, :, 0] = Pinf / s2
+        dPinf[:, :, 1] = [[0, 0, -k2], [0, k2, 0], [-k2, 0, -100 * s2 / l ** 5]]
+    elif kernel == "matern72":
+        dF[3, :, 1] = [196 / l ** 5, 84 * math.sqrt(7) / l ** 4, 84 / l ** 3, 4 * math.sqrt(7) / l ** 2]
+        dQc[0, 0, 0] = 10976 * math.sqrt(7) / 5 / l ** 7; dQc[0, 0, 1] = -s2 * 76832 * math.sqrt(7) / 5 / l ** 8
+        dPinf[:, :, 0] = Pinf / s2
+        dl = np.zeros(16); pv = Pinf.reshape(-1, order="F")         # MATLAB linear (column-major) indexing, :103-106
+        dl[2::3] = -2 * pv[2::3] / l
+        dl[1::3] = -4 * pv[1::3] / l
+        dl[-1] = -3 * 2 * pv[-1] / l
+        dPinf[:, :, 1] = dl.reshape((4, 4), order="F")
+    else:
+        raise ValueError(kernel)
+    return dF, dQc, dPinf
+
+
+def ss_modulators_nmf_derivs(w_subband, w_modulator, kernel1, kernel2):
+    """Derivative stacks of ss_modulators_nmf.m (:25-47, :60-78, :84-110, :127-129): (dF, dQc, dPinf), each with
+    3D + 2N slices ordered [d/dsig1 (D), d/dlen1 (D), d/domega (D), d/dsig2 (N), d/dlen2 (N)]."""
+    w_subband = np.asarray(w_subband, float).ravel()
+    w_modulator = np.asarray(w_modulator, float).ravel()
+    D = w_subband.size // 3
+    N = w_modulator.size // 2
+    sig1, len1 = w_subband[:D], w_subband[D:2 * D]
+    sig2, len2 = w_modulator[:N], w_modulator[N:]
+    tau1 = _CF[kernel1](1.0, 1.0)[0].shape[0]
+    tau3 = _CF[kernel2](1.0, 1.0)[0].shape[0]
+    tau2 = 2
+    nz, ng = tau1 * tau2 * D, tau3 * N
+    n, nq = nz + ng, tau2 * D + N
+    P = 3 * D + 2 * N
+    dF = np.zeros((n, n, P)); dQc = np.zeros((nq, nq, P)); dPinf = np.zeros((n, n, P))
+    I2 = np.eye(tau2)
+    for d in range(D):
+        dFd, dQd, dPd = _cf_derivs(kernel1, sig1[d], len1[d])
+        z = slice(d * tau1 * tau2, (d + 1) * tau1 * tau2)
+        q = slice(d * tau2, (d + 1) * tau2)
+        for which, p in ((0, d), (1, D + d)):                         # kron(dF1, eye(tau2)), :62-69
+            dF[z, z, p] = np.kron(dFd[:, :, which], I2)
+            dQc[q, q, p] = np.kron(dQd[:, :, which], I2)
+            dPinf[z, z, p] = np.kron(dPd[:, :, which], I2)
+        dF[z, z, 2 * D + d] = np.kron(np.eye(tau1), np.array([[0.0, -1.0], [1.0, 0.0]]))      # d/domega, :43-58
+    for j in range(N):
+        dFd, dQd, dPd = _cf_derivs(kernel2, sig2[j], len2[j])
+        g = slice(nz + j * tau3, nz + (j + 1) * tau3)
+        for which, p in ((0, 3 * D + j), (1, 3 * D + N + j)):
+            dF[g, g, p] = dFd[:, :, which]
+            dQc[tau2 * D + j, tau2 * D + j, p] = dQd[0, 0, which]
+            dPinf[g, g, p] = dPd[:, :, which]
+    return dF, dQc, dPinf
+
+
 def lti_disc(F, L=None, Q=None, dt=1.0):
     """lti_disc.m:60-82: A = expm(F dt); Q by matrix-fraction decomposition."""
     n = F.shape[0]
