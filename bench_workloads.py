@@ -238,7 +238,39 @@ def c4_giekf(ctx, T=100000, reps=2, cpu_baseline=True):
         dt = time.perf_counter() - t0
         cpu = {"value": Tc / dt, "unit": "time-steps/s", "cores": 1, "kind": "port",
                "sample": "oracle/giekf.py (NumPy, dense n=%d), first %d samples of the same signal, g_iter=1 (%.1f s)" % (n, Tc, dt)}
-    return {"cpu_baseline": cpu,"workload": "C4: gf_giekf_modulator_nmf predict, D=32 x N=3 (dense n=%d), T=%d, g_iter=1, missing-data gaps, one signal per GPU" % (n, T),
+    grad = None
+    if ctx.rank == 0:
+        # the analytic-gradient mode of the same file (gf_giekf_modulator_nmf.m:296-437, GradObj = 'on'): energy and
+        # 1 + 3D + 2N = 103 sensitivity recursions on a gap-free signal of the same model (a missing sample makes
+        # the reference's energy NaN), through the public entry point with host buffers
+        Tg = min(T, 50000)
+        yg, _, _ = nsagp.synth.sample_signal(hyp, K1, K2, Tg, np.random.default_rng(11))
+        ss_gpu = lambda x, p1, p2, k1, k2: nsagp.ss_modulators_nmf(p1, p2, k1, k2)
+        tg = np.arange(1.0, Tg + 1.0)
+        g_ms, g_wall = None, None
+        for rep in range(2):
+            t0 = time.perf_counter()
+            e, g = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), tg, yg, ss_gpu, None, None, K1, K2, 1, Dk, Nk, 1, 1, GradObj="on")
+            g_wall = time.perf_counter() - t0
+            ms = np.zeros(2)
+            lm.check(L.nsagp_giekf_timings(lm.dptr(ms), 2))
+            g_ms = ms[0]
+        grad = {"workload": "gf_giekf_modulator_nmf nlZ + analytic gradient (GradObj='on'), same model, T=%d, %d parameters = %d CTAs" % (Tg, g.size, g.size),
+                "kernel_ms": g_ms, "steps_per_s": Tg / g_ms * 1e3, "e2e_steps_per_s": Tg / g_wall,
+                "parameter_steps_per_s": g.size * Tg / g_ms * 1e3, "cycles_per_step": g_ms * 1e-3 * sm_hz / Tg,
+                "finite": bool(np.isfinite(e) and np.all(np.isfinite(g)))}
+        if cpu_baseline:
+            from oracle import giekf as ogk, ssmodel as oss
+            Tc = 100
+            ss_ref = lambda x, p1, p2, k1, k2: oss.ss_modulators_nmf(p1, p2, k1, k2) + oss.ss_modulators_nmf_derivs(p1, p2, k1, k2)
+            t0 = time.perf_counter()
+            eo, go = ogk.gf_giekf_modulator_nmf(hyp.pack_log(), tg[:Tc], yg[:Tc], ss_ref, None, None, K1, K2, 1, Dk, Nk, 1, 1, GradObj="on")
+            dt = time.perf_counter() - t0
+            ep, gp = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), tg[:Tc], yg[:Tc], ss_gpu, None, None, K1, K2, 1, Dk, Nk, 1, 1, GradObj="on")
+            grad["cpu_baseline"] = {"value": Tc / dt, "unit": "time-steps/s", "cores": 1, "kind": "port",
+                                    "sample": "oracle/giekf.py giekf_energy_grad (NumPy, dense n=%d, %d parameters incl. the 2n x 2n expm stack), first %d samples (%.1f s)" % (n, go.size, Tc, dt)}
+            grad["gradient_rel_err_vs_oracle_prefix"] = float(np.max(np.abs(gp - go) / np.abs(go)))      # worst ENTRY
+    return {"cpu_baseline": cpu, "gradient_mode": grad, "workload": "C4: gf_giekf_modulator_nmf predict, D=32 x N=3 (dense n=%d), T=%d, g_iter=1, missing-data gaps, one signal per GPU" % (n, T),
             "scaling": "weak", "filter_ms": f_ms, "smoother_ms": s_ms, "steps_per_s": ctx.world * T / (f_ms + s_ms) * 1e3,
             "e2e_steps_per_s": ctx.world * T / wall, "filter_cycles_per_step": f_ms * 1e-3 * sm_hz / T,
             "smoother_dense_equiv_tflops": 12.3 * n ** 3 * T / (s_ms * 1e-3) / 1e12,

@@ -8,7 +8,8 @@ GradObj = 'on') -- csrc/ekfgrad.cuh through the C A
 * the NaN contract and the argument checks.
 
 Tolerance: the recursion is sequential FP64 in both implementations; they differ by the operation order of the
-dense products (the device works block by block), so 1e-8 relative to the largest gradient entry.
+dense products (the device works block by block): 1e-8 relative, ENTRY BY ENTRY (the entries span 15 decades in the
+unbalanced variant, a max-norm would only test the largest; observed <= 6e-12).
 """
 import numpy as np
 import pytest
@@ -44,7 +45,7 @@ def test_giekf_gradient_matches_oracle(nsagp, gpu_lib, D, N, T, k1, k2, balanced
                                           GradObj="on", balance_derivatives=balanced)
     assert go.shape == gg.shape == (1 + 3 * D + 2 * N,)
     assert abs(eg - eo) < TOL * abs(eo)
-    assert np.max(np.abs(gg - go)) < TOL * np.max(np.abs(go)), np.c_[gg, go]
+    assert np.all(np.abs(gg - go) <= TOL * np.abs(go)), np.c_[gg, go]
     # the energy is the one the GradObj = 'off' call reports
     e_off, g_off = nsagp.gf_giekf_modulator_nmf(pb["w"], pb["t"], pb["y"], pb["ss_gpu"], None, None, k1, k2, 1, D, N, 1, 1)
     assert abs(e_off - eg) < 1e-10 * abs(eg) and not np.any(g_off)
