@@ -44,6 +44,9 @@ function mom = nsagp_resolve_mom(mom, N)
     end
   end
   switch likname
+    case 'likModulatorPower'       % the model without NMF weights (demo_toy_modulators.m:88): NMFPower with W = I
+      if ~isfield(ws, 'p_cubature'), error('nsagp:mom', 'the closure does not capture `p_cubature`'); end
+      mom = nsagp_mom('likModulatorNMFPower', shift, ws.p_cubature, N);
     case 'likModulatorNMFPower'
       if ~isfield(ws, 'p_cubature'), error('nsagp:mom', 'the closure does not capture `p_cubature`'); end
       mom = nsagp_mom('likModulatorNMFPower', shift, ws.p_cubature, N);
@@ -53,6 +56,6 @@ function mom = nsagp_resolve_mom(mom, N)
       end
       mom = nsagp_mom('likModulatorPreCalcwn', shift, ws.wn, ws.xn_unscaled);
     otherwise
-      error('nsagp:mom', 'unsupported likelihood %s (likModulatorNMFPower / likModulatorPreCalcwn run on the GPU)', likname);
+      error('nsagp:mom', 'unsupported likelihood %s (likModulatorNMFPower / likModulatorPower / likModulatorPreCalcwn run on the GPU)', likname);
   end
 end

@@ -13,12 +13,12 @@ falls back to the CPU.
 from . import _lib, batch, chunked, cubature, mcrec, ssmodel, synth, tables       # noqa: F401
 from ._lib import NsagpError, build                                       # noqa: F401
 from .cubature import gauher, mvhermgauss_unit, utp_ws                    # noqa: F401
-from .entry import (Plan, gf_ep_modulator_nmf, gf_ep_modulator_nmf_constraints,      # noqa: F401
+from .entry import (Plan, gf_ep_modulator, gf_ep_modulator_nmf, gf_ep_modulator_nmf_constraints,      # noqa: F401
                     gf_giekf_modulator_nmf, gf_giekf_modulator_nmf_constraints,
                     ihgp_ep_modulator_nmf, ihgp_ep_modulator_nmf_constraints,
                     inv_sigmoid, lambda_map, merge_inputs, sigmoid)
 from .mcrec import reconstruct_signal                                     # noqa: F401
-from .lik import Moments, Softplus, likModulatorNMFPower, likModulatorPreCalcwn      # noqa: F401
-from .ssmodel import BlockModel, lti_disc, ss_modulators_nmf, to_block_model         # noqa: F401
+from .lik import Moments, Softplus, likModulatorNMFPower, likModulatorPower, likModulatorPreCalcwn      # noqa: F401
+from .ssmodel import BlockModel, lti_disc, ss_modulators, ss_modulators_nmf, to_block_model         # noqa: F401
 
 __version__ = "0.1.0"

@@ -295,6 +295,29 @@ def gf_ep_modulator_nmf(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, 
                 ep_damping, ep_itts, None, False, nargout, debug_cov, adf_form=adf_form)
 
 
+def gf_ep_modulator(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, ep_fraction, ep_damping, ep_itts,
+                    nargout=6, debug_cov=False, adf_form=0):
+    """Drop-in for matlab/gf_ep_modulator.m, the model WITHOUT NMF weights (demo_toy_modulators.m:99,109): D carrier x
+    modulator pairs, y = sum_d z_d link(g_d).  It is gf_ep_modulator_nmf.m line by line with W = I and N = D (the
+    files differ in the ``mom`` signature, :138,:227), run on the balanced model (:75-81): ``ss(x, param, k1, k2)``
+    takes the five parameter groups in one vector (:69-72), ``mom`` comes from ``likModulatorPower``.  The sigma
+    points live in D dimensions, so D <= 4 pairs (the demo has 2)."""
+    w = np.asarray(w, float).ravel()
+    nlik = int(num_lik_params)
+    if (w.size - nlik) % 5:
+        raise ValueError("w must hold num_lik_params + 5 D entries")
+    pairs = (w.size - nlik) // 5
+    # the NMF entry point's parameter vector: [lik; var1, len1, omega; var2, len2; log W(:)] with W = I
+    with np.errstate(divide="ignore"):
+        w_nmf = np.concatenate([w, np.log(np.eye(pairs).reshape(-1, order="F"))])
+    ss_nmf = lambda x_, p1, p2, k1, k2: ss(x_, np.concatenate([p1, p2]), k1, k2)
+    res = _run(_lib.KIND_FULL, w_nmf, x, y, ss_nmf, mom, xt, kernel1, kernel2, nlik, pairs, pairs, ep_fraction,
+               ep_damping, ep_itts, None, True, nargout, debug_cov, adf_form=adf_form)
+    if not (xt is not None and np.size(xt) > 0):
+        return res[0], np.zeros(w.size)
+    return res
+
+
 def gf_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, D, N,
                                     ep_fraction, ep_damping, ep_itts, constraints, w_fixed, tune_hypers,
                                     nargout=6, debug_cov=False, adf_form=0):

@@ -98,6 +98,14 @@ def likModulatorNMFPower(link, p_cubature, N):
     return Moments(0, link, wn, xn, p=int(p_cubature))
 
 
+def likModulatorPower(link, p_cubature, D):
+    """``mom`` for matlab/likModulatorPower.m, the likelihood of the model without NMF weights (``gf_ep_modulator``,
+    D carrier x modulator pairs): the arithmetic of likModulatorNMFPower with W = I.  One deviation: the floor under
+    the tilted normaliser Z is the NMF files' 1e-10 (csrc/common.cuh kJitter), not this file's 1e-8 (:29) -- it
+    differs only at steps whose Z is below 1e-8."""
+    return likModulatorNMFPower(link, p_cubature, D)
+
+
 def likModulatorPreCalcwn(link, wn, xn_unscaled):
     """``mom`` for matlab/experiments/likModulatorPreCalcwn.m (spectrogram model,
     Power-EP constant, caller-supplied sigma points)."""

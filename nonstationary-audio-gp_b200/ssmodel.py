@@ -156,6 +156,16 @@ def ss_modulators_nmf(w_subband, w_modulator, kernel1, kernel2):
             DerivStack(n, starts, dFs), DerivStack(2 * D + N, qstarts, dQs), DerivStack(n, starts, dPs))
 
 
+def ss_modulators(w, kernel1, kernel2):
+    """``[F,L,Qc,H,Pinf,dF,dQc,dPinf] = ss_modulators(w,kernel1,kernel2)`` (matlab/ss_modulators.m): D carrier x
+    modulator pairs with ``w = [var1; len1; omega; var2; len2]`` -- the construction of ss_modulators_nmf with N = D."""
+    w = np.asarray(w, float).ravel()
+    if w.size % 5:
+        raise ValueError("w must hold [var_fast; len_fast; omega; var_slow; len_slow] for D pairs")
+    D = w.size // 5
+    return ss_modulators_nmf(w[:3 * D], w[3 * D:], kernel1, kernel2)
+
+
 def lti_disc(F, L=None, Qc=None, dt=1.0):
     """``[A,Q] = lti_disc(F,L,Qc,dt)``: A = expm(F dt), Q by matrix-fraction
     decomposition (lti_disc.m:73-82)."""

@@ -96,7 +96,7 @@ def model_from_params(lik_param, param1, param2, ss, x, kernel1, kernel2, do_bal
 
 
 def gf_ep_core(A, Q, H, Pinf, lik_param, Wnmf, yall, mom, ep_fraction, ep_damping, ep_itts,
-               predict, return_ind=None, want_cov=False):
+               predict, return_ind=None, want_cov=False, predict_first=False):
     """The two loops of gf_ep_modulator_nmf.m given the discrete model.
 
     predict=True  -> (Eft, Varft, lb, ub, out)      (:113-352)
@@ -122,7 +122,7 @@ def gf_ep_core(A, Q, H, Pinf, lik_param, Wnmf, yall, mom, ep_fraction, ep_dampin
         run_filter = predict or itt == 1 or itt < ep_itts           # :396
         if run_filter:
             for k in range(T):
-                if k > 0:
+                if k > 0 or (predict and predict_first):          # gf_ep_modulator.m:131-133 predicts at k = 1 too
                     m = A @ m
                     P = A @ P @ A.T + Q
                 if not np.isnan(yall[k]):
@@ -230,4 +230,30 @@ def gf_ep_modulator_nmf_constraints(w, x, y, ss, mom, xt, kernel1, kernel2, num_
                                              ep_damping, ep_itts, True, return_ind, want_cov)
         return Eft, Varft, None, lb, ub, out
     edata, out = gf_ep_core(A, Q, H, Pinf, lik_param, Wnmf, yall, mom, ep_fraction, ep_damping, ep_itts, False)
+    return edata, np.zeros(np.size(w))
+
+
+def gf_ep_modulator(w, x, y, ss, mom, xt, kernel1, kernel2, num_lik_params, ep_fraction, ep_damping, ep_itts,
+                    want_cov=False):
+    """gf_ep_modulator.m:1 -- the model WITHOUT the NMF weights: D carrier x modulator pairs, y = sum_d z_d link(g_d)
+    (demo_toy_modulators.m).  Same two loops as gf_ep_modulator_nmf.m with W = I (the line-by-line difference is the
+    ``mom`` signature, :138,:227), on the BALANCED model (:75-81), the prediction also at k = 1 in predict mode
+    (:131-133; a no-op on the stationary initial state), ``ss(x, param, kernel1, kernel2)`` with the five parameter
+    groups in one vector (:69-72) and ``mom(hyp, mu, s2, ep_frac, yall, k)`` without W."""
+    yall, return_ind = merge_inputs(x, y, xt)
+    w = np.asarray(w, float).ravel()
+    lik_param = w[:num_lik_params]
+    param = np.exp(w[num_lik_params:])
+    F, L, Qc, H, Pinf = ss(x, param, kernel1, kernel2)[:5]
+    F, L, H, Pinf, _ = ssmodel.balance_ss(F, L, H, Pinf)
+    A, Q = ssmodel.lti_disc(F, L, Qc, 1.0)
+    pairs = H.shape[0] // 2
+    Wid = np.eye(pairs)
+    mom_w = lambda hyp, mu, s2, nmfW, ep_frac, yall_, k: mom(hyp, mu, s2, ep_frac, yall_, k)
+    predict = xt is not None and np.size(xt) > 0
+    if predict:
+        Eft, Varft, lb, ub, out = gf_ep_core(A, Q, H, Pinf, lik_param, Wid, yall, mom_w, ep_fraction, ep_damping, ep_itts,
+                                             True, return_ind, want_cov, predict_first=True)
+        return Eft, Varft, None, lb, ub, out
+    edata, out = gf_ep_core(A, Q, H, Pinf, lik_param, Wid, yall, mom_w, ep_fraction, ep_damping, ep_itts, False)
     return edata, np.zeros(np.size(w))

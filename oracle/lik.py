@@ -24,8 +24,7 @@ def _normpdf(y, mu, sigma):
     return np.exp(-0.5 * ((y - mu) / sigma) ** 2) / (math.sqrt(2 * math.pi) * sigma)
 
 
-def _moments(link_xn_W, xn, wn, y, mu_z, mu_g, s2_z, s2_g, sn2, ep_fraction, pEP_const):
-    jitter = 1e-10
+def _moments(link_xn_W, xn, wn, y, mu_z, mu_g, s2_z, s2_g, sn2, ep_fraction, pEP_const, jitter=1e-10):
     D = mu_z.size
     N = mu_g.size
     sn2_link_xn2_s2_z = sn2 / ep_fraction + (link_xn_W ** 2) @ s2_z      # :45
@@ -79,6 +78,23 @@ def likModulatorNMFPower(link, hyp, y, mu, s2, W, p, ep_fraction):
     with np.errstate(all="ignore"):
         link_xn_W = link(xn) @ W.T                                            # :44
         return _moments(link_xn_W, xn, wn, y, mu_z, mu_g, s2_z, s2_g, sn2, ep_fraction, 1.0)   # pEP_const = 1 (:49)
+
+
+def likModulatorPower(link, hyp, y, mu, s2, p, ep_fraction):
+    """likModulatorPower.m:28-90: the likelihood of the model without NMF weights, y = sum_d z_d link(g_d) -- the
+    arithmetic of likModulatorNMFPower with W = I (D pairs, mu = [mu_z; mu_g]) and a floor of 1e-8 (:29) under Z."""
+    sn2 = math.exp(float(np.asarray(hyp).ravel()[0]))
+    mu = np.asarray(mu, float).ravel(); s2 = np.asarray(s2, float).ravel()
+    D = mu.size // 2
+    mu_z, mu_g = mu[:D], mu[D:]
+    s2_z, s2_g = s2[:D], s2[D:]
+    if p in (3, 5, 7, 9):
+        wn, xn_unscaled = cubature.utp_ws(p, D)                                # :34
+        xn = _points(mu_g, s2_g, xn_unscaled)
+    else:
+        xn, wn = cubature.mvhermgauss(mu_g, s2_g, p)
+    with np.errstate(all="ignore"):
+        return _moments(link(xn), xn, wn, y, mu_z, mu_g, s2_z, s2_g, sn2, ep_fraction, 1.0, jitter=1e-8)
 
 
 def likModulatorPreCalcwn(link, hyp, y, mu, s2, W, ep_fraction, wn, xn_unscaled):

@@ -118,6 +118,14 @@ def ss_modulators_nmf(w_subband, w_modulator, kernel1, kernel2):
     return F, L, Qc, H, Pinf
 
 
+def ss_modulators(w, kernel1, kernel2):
+    """ss_modulators.m:1-134: D carrier x modulator pairs, one parameter vector [var1; len1; omega; var2; len2] (:5-10).
+    Line by line the construction of ss_modulators_nmf.m with N = D."""
+    w = np.asarray(w, float).ravel()
+    D = w.size // 5
+    return ss_modulators_nmf(w[:3 * D], w[3 * D:], kernel1, kernel2)
+
+
 def _cf_derivs(kernel, magnSigma2, lengthScale):
     """Derivative stacks (dF, dQc, dPinf), last axis = (magnSigma2, lengthScale), of one covariance function:
     cf_exp_to_ss.m:70-92, cf_matern32_to_ss.m:78-104, cf_matern52_to_ss.m:82-112, cf_matern72_to_ss.m:84-116."""
