@@ -65,6 +65,14 @@ def _model(nsagp, hyp, k1, k2, D_, N_, ihgp, smoother=True):
     return mdl, (nsagp.tables.build_tables(mdl, want_smoother=smoother) if ihgp else None)
 
 
+def _hbm_peak():
+    try:
+        import json, os
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0                      # the profiling guide's fallback
+
+
 def _mom(nsagp):
     wn, xn = nsagp.utp_ws(P_CUB, N)
     return nsagp.likModulatorPreCalcwn(nsagp.Softplus(SHIFT), wn, xn)
@@ -116,6 +124,17 @@ def one_signal_chunked(ctx, kind, T, itts, seed, reps=2, warm=1, chunks_per_gpu=
     res["parallel_first_pass"] = {"first_pass": "burn-in overlap: %d chunks per GPU, %d steps of burn-in each (opt-in, approximate)" % (chunks_per_gpu, burnin),
                                   "ms": ms, "steps_per_s": units / ms * 1e3, "phases_ms": ph,
                                   "boundary_mismatch_rel": mis / scale if scale > 0 else None}
+    if ihgp:
+        # the frozen-site passes against the HBM roof (SURVEY 8d / BASELINE.md 4: 8 + 24 n + 88 M algorithmic bytes per time
+        # step and filter+smoother sweep); a run has itts - 1 frozen filter passes and itts smoother passes
+        bps = 8 + 24 * mdl.n + 88 * mdl.M
+        sweeps = (2 * itts - 1) / 2.0
+        frozen_ms = ph["fixed_filter"] + ph["smoother"]
+        gbs = bps * (T / ctx.world) * sweeps / (frozen_ms * 1e-3) / 1e9
+        res["frozen_sweep_roofline"] = {"bound": "hbm", "kernels": "scan_reduce2 / scan_apply2_kernel<FilterElem | SmootherElem> + carry",
+                                        "algorithmic_bytes_per_step_and_sweep": bps, "achieved": gbs, "unit": "GB/s per GPU",
+                                        "peak": _hbm_peak(), "frac": gbs / _hbm_peak(),
+                                        "ms_per_sweep": frozen_ms / sweeps}
     if exact:
         nlz_par = plan.fetch(0, ("nlZ",))["nlZ"]
         res["parallel_first_pass"]["nlZ_rel_dev_vs_exact"] = float(np.max(np.abs(nlz_par - nlz_exact) / np.abs(nlz_exact)))

@@ -200,7 +200,8 @@ int nsagp_giekf_carry(const nsagp_model* model, const double* W, double sigma2, 
  *   dPinf[j] = the initial dP_j                               (:314)
  * each a bmax-by-bmax column-major block, bmax = max(bz, bg), zero padded; dR[j] = d sigma2 / d theta_j (:96).
  * Out: edata[1], gdata[nparam] BEFORE the log-scale factor exp(w) of :432-433.  NaN + NSAGP_ERR_NAN as nsagp_giekf.
- * One CTA per parameter, P and dP_j in shared memory: needs 2 n^2 doubles <= ~220 KB (n <= ~115). */
+ * One CTA per parameter with P and dP_j in shared memory (2 n^2 doubles <= ~220 KB: n <= ~115); for larger n (<= 160;
+ * C4's matern32 shape, n = 137) dP_j is kept in an HBM scratch instead -- same arithmetic, slower. */
 int nsagp_giekf_grad(const nsagp_model* model, const double* W, double sigma2, int32_t nparam, const int32_t* latent,
                      const double* dA, const double* dQ, const double* dPinf, const double* dR, const double* y, int64_t T,
                      double* edata, double* gdata);
@@ -304,10 +305,20 @@ int nsagp_plan_adf_mismatch(nsagp_plan* plan, double* out2);
  * and lik_quad = sum over observed steps of v^2 / (2 S) (:99); the caller adds the constant part (:80). */
 int nsagp_fastfb(int32_t n, const double* A, const double* AKHA, const double* Kg, const double* HA, double S,
                  const double* G, const double* y, int64_t T, double* MS, double* lik_quad);
-/* Tuning knob of the frozen-site scans (csrc/scan.cuh): signals of at least `family_min_steps` steps run the subband
- * and the modulator latents as two launches per phase, each computing at its own block size (default 400 000; 0 =
- * always, used by the parity tests).  Results agree to rounding either way. */
+/* Tuning knobs of the frozen-site scans (csrc/scan.cuh): signals of at least `family_min_steps` steps run the subband
+ * and the modulator latents each at its own block size instead of the padded one (default 0 = always).  nsagp_scan_merge: 1 (default) = the two families share one CTA tile, whole warps per family, one launch
+ * per phase; 0 = one launch per family and phase (the earlier form, kept for comparison).  Results agree to rounding
+ * in every combination. */
 int nsagp_scan_config(int64_t family_min_steps);
+int nsagp_scan_merge(int32_t on);
+/* 1 (default) = every CTA tile of a scan starts by bulk-prefetching its input rows into L2 (cp.async.bulk.prefetch.L2);
+ * 0 = off.  No effect on results. */
+int nsagp_scan_prefetch(int32_t on);
+/* Form of the smoother-side site update (csrc/siteupd.cuh): 0 (default) = four lanes per time step, sigma points two at
+ * a time when the rule has few distinct coordinates (every utp_ws rule), else one at a time; 2 = always one at a time;
+ * 1 = the first-generation kernel, one thread per step (csrc/ihgp.cuh).  The environment variable NSAGP_SITE_FORM sets
+ * the initial value.  Kept as independent cross-checks; results agree to rounding. */
+int nsagp_site_config(int32_t form);
 /* Device time (ms, CUDA events on the launch stream) of the phases of the last
  * nsagp_plan_run: [0] total, [1] ADF filter pass, [2] fixed-site filter passes,
  * [3] smoother passes, [4] site-update passes.  Returns the number written. */

@@ -671,10 +671,27 @@ int nsagp_plan_keep_pf(nsagp_plan* pl, int keep) {
   return NSAGP_OK;
 }
 
-long long g_fam_min_steps = 400000;             // see DISPATCH_FAM below
+long long g_fam_min_steps = 0;                  // see DISPATCH_FAM below
 int nsagp_scan_config(int64_t family_min_steps) {
   if (family_min_steps < 0) return fail(NSAGP_ERR_INVALID, "family_min_steps must be >= 0");
   g_fam_min_steps = family_min_steps;
+  return NSAGP_OK;
+}
+
+int g_site_form = std::getenv("NSAGP_SITE_FORM") ? std::atoi(std::getenv("NSAGP_SITE_FORM")) : 0;
+int nsagp_site_config(int32_t form) {
+  if (form < 0 || form > 2) return fail(NSAGP_ERR_INVALID, "site-update form must be 0, 1 or 2");
+  g_site_form = form;
+  return NSAGP_OK;
+}
+
+int g_scan_merge = 1, g_scan_l2pf = 1;
+int nsagp_scan_merge(int32_t on) {
+  g_scan_merge = on ? 1 : 0;
+  return NSAGP_OK;
+}
+int nsagp_scan_prefetch(int32_t on) {
+  g_scan_l2pf = on ? 1 : 0;
   return NSAGP_OK;
 }
 
@@ -910,8 +927,10 @@ template <class EZ_, class EG_> struct ElemPair { using EZ = EZ_; using EG = EG_
 
 // Specialised pairs for the block-size combinations of the reference's kernels that matter (exp / matern32 / matern52
 // subbands with matern52 modulators); everything else computes both families at the padded size.
-// (On short signals -- below g_fam_min_steps steps -- the second launch per phase and the small modulator-family CTAs cost
-// more than the subband family saves: C2 at T = 1e5 was 2 ms slower per EP run; there both families run padded.)
+// (nsagp_scan_config: signals below g_fam_min_steps steps run both families padded.  With one launch per family the
+// second launch and the small modulator-family CTAs cost more than the subband family saved on short signals -- C2 at
+// T = 1e5 was 2 ms slower per EP run, hence a threshold of 400 000 steps; with both families in one CTA tile the
+// specialised form wins at every length, profiles/r2l_ab.jsonl, and the default threshold is 0.)
 #define DISPATCH_FAM(PL, ELEMT, ...)                                                                           \
   do {                                                                                                         \
     const bool fam_ = (PL)->T >= g_fam_min_steps;                                                              \
@@ -926,29 +945,42 @@ template <class EZ_, class EG_> struct ElemPair { using EZ = EZ_; using EG = EG_
     else { using Pair_ = ElemPair<ELEMT<8, 8>, ELEMT<8, 8>>; __VA_ARGS__; }                                     \
   } while (0)
 
+// Distinct element types per family: one CTA tile runs both (scan_reduce2 / scan_apply2_kernel, whole warps per family);
+// nsagp_scan_merge(0) launches each family on its own instead (the form measured in profiles/r2i_*, kept for comparison).
+static bool scan_merge() { return g_scan_merge != 0; }
+
 template <class Pair>
 int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags) {
-  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.flags = flags; a.nprev = 0;
-  a.CH = scan_ch(pl, Pair::EZ::kMapDoubles, ScanBounds<typename Pair::EZ>::kThreads, std::is_same<typename Pair::EZ, typename Pair::EG>::value ? pl->M : std::max(pl->D, pl->N));
-  // a CTA tile of M*CH threads must fit an SM (registers, shared memory): ask the occupancy calculator
+  a.kfirst = kfirst; a.nsteps = nsteps; a.dir = dir; a.init = init; a.kinit = kinit; a.nprev = 0;
+  a.flags = flags | (g_scan_l2pf ? kScanFlagL2Prefetch : 0);
+  constexpr bool same = std::is_same<typename Pair::EZ, typename Pair::EG>::value;
+  const bool merge = !same && scan_merge();
+  const int maxthr = ScanBounds<typename Pair::EZ>::kThreads;
+  a.CH = scan_ch(pl, Pair::EZ::kMapDoubles, maxthr, same || merge ? pl->M : std::max(pl->D, pl->N));
+  while (merge && a.CH > 1 && scan2_threads(pl->D, pl->N, a.CH) > maxthr) --a.CH;
   // a CTA tile of (family latents)*CH threads must fit an SM (registers, shared memory): ask the occupancy calculator
   // for both families' kernels -- they share the tile geometry, because they share the buffers
   auto fits = [&](int ch) {
-    auto ok = [&](auto red, auto app, int lat) {
+    auto ok = [&](auto red, auto app, int lat, int threads) {
       const size_t sm1 = (size_t)ch * lat * Pair::EZ::kMapDoubles * sizeof(double);
       const size_t sm3 = (size_t)ch * lat * (Pair::EZ::kStateDoubles + Pair::EZ::kMapDoubles) * sizeof(double);
       if (sm1 > 48 * 1024) cudaFuncSetAttribute(red, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
       if (sm3 > 48 * 1024) cudaFuncSetAttribute(app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
       int n1 = 0, n3 = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, red, lat * ch, sm1) != cudaSuccess) n1 = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, app, lat * ch, sm3) != cudaSuccess) n3 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, red, threads, sm1) != cudaSuccess) n1 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n3, app, threads, sm3) != cudaSuccess) n3 = 0;
       cudaGetLastError();
       return n1 >= 1 && n3 >= 1;
     };
-    if (std::is_same<typename Pair::EZ, typename Pair::EG>::value)
-      return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->M);
-    return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->D) &&
-           ok(scan_reduce_kernel<typename Pair::EG>, scan_apply_kernel<typename Pair::EG>, pl->N);
+    if constexpr (same) {
+      return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->M, pl->M * ch);
+    } else {
+      if (merge)
+        return ok(scan_reduce2_kernel<typename Pair::EZ, typename Pair::EG>, scan_apply2_kernel<typename Pair::EZ, typename Pair::EG>,
+                  pl->M, scan2_threads(pl->D, pl->N, ch));
+      return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->D, pl->D * ch) &&
+             ok(scan_reduce_kernel<typename Pair::EG>, scan_apply_kernel<typename Pair::EG>, pl->N, pl->N * ch);
+    }
   };
   while (a.CH > 1 && !fits(a.CH)) --a.CH;
   return NSAGP_OK;
@@ -968,8 +1000,14 @@ int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
     return NSAGP_OK;
   };
   int rcl;
-  if (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
+  if constexpr (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
     if ((rcl = launch(scan_reduce_kernel<typename Pair::EZ>, 0, pl->M))) return rcl;
+  } else if (scan_merge()) {
+    auto kern = scan_reduce2_kernel<typename Pair::EZ, typename Pair::EG>;
+    const size_t sm1 = (size_t)a.CH * pl->M * Pair::EZ::kMapDoubles * sizeof(double);
+    if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    kern<<<grid, scan2_threads(pl->D, pl->N, a.CH), sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile);
+    LAUNCH_CHECK();
   } else {
     if ((rcl = launch(scan_reduce_kernel<typename Pair::EZ>, 0, pl->D)) || (rcl = launch(scan_reduce_kernel<typename Pair::EG>, pl->D, pl->N))) return rcl;
   }
@@ -1035,8 +1073,14 @@ int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev, 
       return NSAGP_OK;
     };
     int rcl;
-    if (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
+    if constexpr (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
       if ((rcl = launch(scan_apply_kernel<typename Pair::EZ>, 0, pl->M))) return rcl;
+    } else if (scan_merge()) {
+      auto kern = scan_apply2_kernel<typename Pair::EZ, typename Pair::EG>;
+      const size_t sm3 = (size_t)a.CH * pl->M * (Pair::EZ::kStateDoubles + Pair::EZ::kMapDoubles) * sizeof(double);
+      if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+      kern<<<grid, scan2_threads(pl->D, pl->N, a.CH), sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start);
+      LAUNCH_CHECK();
     } else {
       if ((rcl = launch(scan_apply_kernel<typename Pair::EZ>, 0, pl->D)) || (rcl = launch(scan_apply_kernel<typename Pair::EG>, pl->D, pl->N))) return rcl;
     }
@@ -1060,12 +1104,13 @@ int affine_scan(nsagp_plan* pl, long long kfirst, long long nsteps, int dir, int
   return rc;
 }
 
-// Smoother-side site update over steps [k0, k1): four lanes per step (siteupd.cuh); NSAGP_SITE_FORM=1 selects the
-// first-generation one-thread-per-step kernel (kept as an independent cross-check).
+// Smoother-side site update over steps [k0, k1): four lanes per step (siteupd.cuh), sigma points two at a time when every
+// problem of the plan has the link table of distinct coordinates; NSAGP_SITE_FORM=2 forces the one-point-at-a-time form,
+// NSAGP_SITE_FORM=1 selects the first-generation one-thread-per-step kernel (both kept as independent cross-checks).
 template <bool FULL>
 int site_update_launch(nsagp_plan* pl, double damp, int write_lZ, int clamp_R, long long k0, long long k1) {
-  static const bool old_form = std::getenv("NSAGP_SITE_FORM") && std::atoi(std::getenv("NSAGP_SITE_FORM")) == 1;
-  if (old_form) {
+  const int form = g_site_form;
+  if (form == 1) {
     constexpr int TPB = 64;
     const size_t sm = (size_t)4 * pl->M * TPB * sizeof(double) + lik_smem_bytes(pl) + site_tab_bytes(pl, TPB);
     const dim3 grid((unsigned)((k1 - k0 + TPB - 1) / TPB), pl->B);
@@ -1077,12 +1122,13 @@ int site_update_launch(nsagp_plan* pl, double damp, int write_lZ, int clamp_R, l
     LAUNCH_CHECK();
     return NSAGP_OK;
   }
-  int nd = 0;
-  for (const DevProblem& P : pl->h_probs) nd = std::max(nd, P.ndist);
+  int nd = 0, nd_min = 1 << 30;
+  for (const DevProblem& P : pl->h_probs) { nd = std::max(nd, P.ndist); nd_min = std::min(nd_min, P.ndist); }
+  const bool pair = form != 2 && nd_min > 0;
   const size_t sm = (size_t)site4_smem_doubles(pl->M, pl->S, nd, FULL) * sizeof(double);
   const dim3 grid((unsigned)((k1 - k0 + kSiteSteps - 1) / kSiteSteps), pl->B);
   DISPATCH_DPT((pl->D <= 16) ? 4 : 8, {
-    auto kern = site_update4_kernel<DPT_, FULL>;
+    auto kern = pair ? site_update4_kernel<DPT_, FULL, true> : site_update4_kernel<DPT_, FULL, false>;
     if (sm > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     kern<<<grid, kSiteThreads, sm, g_stream>>>(pl->d_probs, pl->d_states, k0, k1, pl->alpha, damp, write_lZ, clamp_R);
   });

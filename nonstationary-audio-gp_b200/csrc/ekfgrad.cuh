@@ -36,11 +36,12 @@ struct EkfGradArgs {
   const double* dP0;       // [nparam][BM*BM] block of dPinf_j                   (:314)
   const double* dR;        // [nparam]                                           (:96)
   double* gdata;           // [nparam] gradient BEFORE the log-scale factor of :432-433
+  double* dP_hbm;          // [nparam][n*n] or null: dP_j kept in HBM / L2 when 2 n^2 doubles exceed the shared memory (n > ~115)
 };
 
-inline size_t ekf_grad_smem_doubles(int n, int M, int BM, int D, int N) {
+inline size_t ekf_grad_smem_doubles(int n, int M, int BM, int D, int N, bool dp_in_smem = true) {
   const int parts = std::max(1, kEgMaxThreads / n);
-  return 2 * (size_t)n * n + 2 * (size_t)M * BM * BM + 2 * BM * BM + (size_t)M * BM + (size_t)D * N + 13 * (size_t)n +
+  return (dp_in_smem ? 2 : 1) * (size_t)n * n + 2 * (size_t)M * BM * BM + 2 * BM * BM + (size_t)M * BM + (size_t)D * N + 13 * (size_t)n +
          3 * (size_t)parts * n + 5 * (size_t)M + 5 * (size_t)N + 5 * 10 + 8;
 }
 
@@ -114,8 +115,10 @@ __global__ void __launch_bounds__(EgCfg<BM>::TH, 1) giekf_grad_kernel(EkfGradArg
   const int parts = max(1, nth / n);
   extern __shared__ __align__(16) double sm[];
   double* P = sm;                              // [n*n] column-major
-  double* dP = P + (size_t)n * n;              // [n*n]
-  double* sA = dP + (size_t)n * n;             // [M][BM*BM]
+  // dP_j [n*n]: shared memory, or (state dimensions whose 2 n^2 doubles do not fit) this parameter's slice of an HBM
+  // scratch -- 150 KB at n = 137, re-read every step, so it lives in L2; same code, slower
+  double* dP = g.dP_hbm ? g.dP_hbm + (size_t)j * n * n : P + (size_t)n * n;
+  double* sA = P + (size_t)(g.dP_hbm ? 1 : 2) * n * n;   // [M][BM*BM]
   double* sQ = sA + M * BM * BM;
   double* sdA = sQ + M * BM * BM;              // [BM*BM]
   double* sdQ = sdA + BM * BM;

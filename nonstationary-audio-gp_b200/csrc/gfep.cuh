@@ -450,6 +450,16 @@ struct RtsScanElem {
   // phase was bound by two exposed HBM round trips per step (issue slots 2-3 % busy, profiles/r2h_*).
   static constexpr bool kTwoTiles = false;
   static constexpr int kPrefetch = BM <= 2 ? 3 : 2;
+  // rows [k_lo, k_hi) of the inputs towards L2 (scan.cuh: scan_tile_prefetch)
+  __device__ static __forceinline__ void prefetch_rows(const DevProblem& P, const DevState& St, long long k_lo, long long k_hi, bool apply) {
+    const size_t rows = (size_t)(k_hi - k_lo);
+    l2_prefetch_bulk(St.PS + (size_t)k_lo * P.M * BMS * BMS, rows * P.M * BMS * BMS * sizeof(double));
+    l2_prefetch_bulk(St.MS + k_lo * P.n, rows * P.n * sizeof(double));
+    if (apply) {
+      l2_prefetch_bulk(St.E + k_lo * P.M, rows * P.M * sizeof(double));
+      l2_prefetch_bulk(St.V + k_lo * P.M, rows * P.M * sizeof(double));
+    }
+  }
   struct In { double PSk[BM * BM], ms[BM], Eold, Vold; };
   struct Tab {};
   bool applying = false;
@@ -704,6 +714,11 @@ struct KfScanElem {
     tt = St.ttau[k * P.M + n]; tn = St.tnu[k * P.M + n];
     if (nlz) tt = fmax(tt, 0.0);
     return true;
+  }
+  __device__ static __forceinline__ void prefetch_rows(const DevProblem& P, const DevState& St, long long k_lo, long long k_hi, bool) {
+    const size_t bytes = (size_t)(k_hi - k_lo) * P.M * sizeof(double);
+    l2_prefetch_bulk(St.ttau + k_lo * P.M, bytes);
+    l2_prefetch_bulk(St.tnu + k_lo * P.M, bytes);
   }
   // (no register-pipelined inputs for this element: scan.cuh scan_walk)
   static constexpr bool kTwoTiles = false;

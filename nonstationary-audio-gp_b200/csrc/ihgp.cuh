@@ -284,6 +284,14 @@ struct FilterElem : AffineElemBase<BMS, BM> {
 #pragma unroll
     for (int i = 0; i < BM; ++i) hA[i] = P.hA[n * BMS + i];
   }
+  // rows [k_lo, k_hi) of the inputs towards L2 (scan.cuh: scan_tile_prefetch); the look-up reads one step back
+  __device__ static __forceinline__ void prefetch_rows(const DevProblem& P, const DevState& St, long long k_lo, long long k_hi, bool) {
+    const long long k0 = k_lo > 0 ? k_lo - 1 : 0;
+    const size_t bytes = (size_t)(k_hi - k0) * P.M * sizeof(double);
+    l2_prefetch_bulk(St.ttau + k0 * P.M, bytes);
+    l2_prefetch_bulk(St.tnu + k0 * P.M, bytes);
+    l2_prefetch_bulk(St.R + k0 * P.M, bytes);
+  }
   // Inputs of step k: the sites of steps k and k-1 (the look-up uses R(:,k-1), :239); table row of the look-up.
   static constexpr int kPrefetch = 3;
   struct In { double tt, tn, R, ttp, Rp; };
@@ -362,6 +370,11 @@ struct SmootherElem : AffineElemBase<BMS, BM> {
     for (int i = 0; i < BM * BM; ++i) A[i] = P.A[n * BMS * BMS + (i % BM) + (i / BM) * BMS];
 #pragma unroll
     for (int i = 0; i < BM; ++i) hv[i] = P.h[n * BMS + i];
+  }
+  __device__ static __forceinline__ void prefetch_rows(const DevProblem& P, const DevState& St, long long k_lo, long long k_hi, bool apply) {
+    l2_prefetch_bulk(St.R + k_lo * P.M, (size_t)(k_hi - k_lo) * P.M * sizeof(double));
+    l2_prefetch_bulk(St.MS + k_lo * P.n, (size_t)(k_hi - k_lo) * P.n * sizeof(double));
+    if (apply) l2_prefetch_bulk(St.E + k_lo * P.M, (size_t)(k_hi - k_lo) * P.M * sizeof(double));
   }
   // Inputs of step k: R(:,k) (look-up of the smoother gain), the filtered mean, H*MS of the previous iteration.
   static constexpr int kPrefetch = 3;

@@ -38,6 +38,37 @@ struct ScanArgs {
   int nprev;                       // carry only: aggregates of preceding shards (other GPUs) placed before the tiles
 };
 
+// ScanArgs::flags bit 8: at the start of a CTA tile one thread asks the memory system to bring the tile's input rows --
+// contiguous in HBM, CH * 32 steps per array -- into L2 with bulk prefetches (cp.async.bulk.prefetch.L2).  The walks
+// below are dependent chains of 32 steps per thread whose loads are issued a few steps ahead; with the rows already on
+// their way to L2 a step waits for an L2 hit instead of an HBM round trip.  Elements opt in by defining prefetch_rows.
+constexpr int kScanFlagL2Prefetch = 256;
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, size_t bytes) {
+  const unsigned long long a0 = (unsigned long long)p & ~15ull;
+  const unsigned long long a1 = ((unsigned long long)p + bytes + 15ull) & ~15ull;
+  for (unsigned long long a = a0; a < a1; a += 1u << 20) {             // (any size works; keep a request below 1 MiB)
+    const unsigned n = (unsigned)((a1 - a < (1u << 20)) ? a1 - a : (1u << 20));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+  }
+}
+
+__device__ __forceinline__ void scan_tile_range(const ScanArgs& a, long long tile, long long& k_lo, long long& k_hi) {
+  const long long s0 = tile * a.CH * kScanSteps;
+  const long long s1 = (s0 + (long long)a.CH * kScanSteps < a.nsteps) ? s0 + (long long)a.CH * kScanSteps : a.nsteps;
+  if (a.dir > 0) { k_lo = a.kfirst + s0; k_hi = a.kfirst + s1; }
+  else { k_lo = a.kfirst - s1 + 1; k_hi = a.kfirst - s0 + 1; }
+}
+
+template <class Elem>
+__device__ __forceinline__ void scan_tile_prefetch(const DevProblem& P, const DevState& St, const ScanArgs& a, bool apply) {
+  if ((a.flags & kScanFlagL2Prefetch) && threadIdx.x == 0) {
+    long long k_lo, k_hi;
+    scan_tile_range(a, blockIdx.x, k_lo, k_hi);
+    if (k_hi > k_lo) Elem::prefetch_rows(P, St, k_lo, k_hi, apply);
+  }
+}
+
 __host__ __device__ inline long long scan_num_chunks(long long nsteps) { return (nsteps + kScanSteps - 1) / kScanSteps; }
 __host__ __device__ inline long long scan_num_tiles(long long nsteps, int CH) {
   const long long per = (long long)kScanSteps * CH;
@@ -140,6 +171,7 @@ scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
   const int M = P.M, CH = a.CH;
   const ScanThread th(threadIdx.x, n0, cnt_lat, CH);
   const int n = th.n, c = th.c;
+  scan_tile_prefetch<Elem>(P, St, a, false);
   extern __shared__ double sm[];                 // [CH][cnt_lat][W]: this family's latents only
   const long long nchunks = scan_num_chunks(a.nsteps);
   const long long ntiles = scan_num_tiles(a.nsteps, CH);
@@ -153,6 +185,61 @@ scan_reduce_kernel(const DevProblem* __restrict__ probs, const DevState* __restr
     const long long first = (long long)blockIdx.x * CH;
     const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
     scan_tile_compose_thread<Elem>(sm, n - n0, cnt_lat, cnt, tile_buf + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + n) * W);
+  }
+}
+
+// Both latent families in ONE CTA tile, each with its own element type: threads [0, CH * D) (rounded up to whole warps)
+// are the subband family, the threads after them the modulators, so no warp mixes the two walks.  Against one launch per
+// family (above) the tile's rows of the site arrays -- M contiguous doubles per step, of which a family reads its share --
+// are fetched from HBM once instead of once per family (the second family's sectors hit L1 / L2), and the small
+// modulator-family CTAs (CH * N threads) no longer run on their own.  Shared memory: [CH][D][W] | [CH][N][W].
+struct ScanThread2 {
+  int n, c, n0, cnt, ftid, fthreads;
+  bool live, fam_g;
+  size_t sm_off;                   // offset of the family's region, in units of (its slot size) doubles per (chunk, latent)
+  __device__ __forceinline__ ScanThread2(int tid, int D, int N, int CH) {
+    const int zthreads = (CH * D + 31) & ~31;
+    fam_g = tid >= zthreads;
+    ftid = fam_g ? tid - zthreads : tid;
+    n0 = fam_g ? D : 0;
+    cnt = fam_g ? N : D;
+    fthreads = fam_g ? (int)blockDim.x - zthreads : zthreads;
+    c = ftid / cnt;
+    n = n0 + (ftid - c * cnt);
+    live = ftid < CH * cnt;
+    sm_off = fam_g ? (size_t)CH * D : 0;
+  }
+};
+__host__ __device__ inline int scan2_threads(int D, int N, int CH) { return ((CH * D + 31) & ~31) + CH * N; }
+
+template <class EZ, class EG>
+__global__ void __launch_bounds__(ScanBounds<EZ>::kThreads, ScanBounds<EZ>::kMinBlocks)
+scan_reduce2_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                    ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf) {
+  constexpr int W = EZ::kMapDoubles;
+  const DevProblem& P = probs[blockIdx.y];
+  const DevState& St = states[blockIdx.y];
+  const int M = P.M, CH = a.CH;
+  const ScanThread2 th(threadIdx.x, P.D, P.N, CH);
+  scan_tile_prefetch<EZ>(P, St, a, false);
+  extern __shared__ double sm[];
+  double* smf = sm + th.sm_off * W;
+  const long long nchunks = scan_num_chunks(a.nsteps);
+  const long long ntiles = scan_num_tiles(a.nsteps, CH);
+  const long long chunk = (long long)blockIdx.x * CH + th.c;
+  if (th.live && chunk < nchunks) {
+    double* cslot = chunk_buf + (((size_t)blockIdx.y * nchunks + chunk) * M + th.n) * W;
+    double* sslot = smf + ((size_t)th.c * th.cnt + (th.n - th.n0)) * W;
+    if (th.fam_g) scan_reduce_thread<EG>(P, St, a, th.n, th.c, chunk, cslot, sslot);
+    else scan_reduce_thread<EZ>(P, St, a, th.n, th.c, chunk, cslot, sslot);
+  }
+  __syncthreads();
+  if (th.live && th.c == 0) {
+    const long long first = (long long)blockIdx.x * CH;
+    const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
+    double* tslot = tile_buf + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + th.n) * W;
+    if (th.fam_g) scan_tile_compose_thread<EG>(smf, th.n - th.n0, th.cnt, cnt, tslot);
+    else scan_tile_compose_thread<EZ>(smf, th.n - th.n0, th.cnt, cnt, tslot);
   }
 }
 
@@ -335,6 +422,7 @@ scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   const int M = P.M, CH = a.CH;
   const ScanThread th(threadIdx.x, n0, cnt_lat, CH);
   const int n = th.n, c = th.c;
+  scan_tile_prefetch<Elem>(P, St, a, true);
   extern __shared__ double sm[];                 // [CH][cnt_lat][SW] states entering each chunk | [CH][cnt_lat][W] chunk maps
   const long long nchunks = scan_num_chunks(a.nsteps);
   const long long ntiles = scan_num_tiles(a.nsteps, CH);
@@ -359,6 +447,46 @@ scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   const long long chunk = first + c;
   if (!th.live || chunk >= nchunks) return;
   scan_apply_thread<Elem>(P, St, a, n, chunk, s_state + ((size_t)c * cnt_lat + (n - n0)) * SW);
+}
+
+template <class EZ, class EG>
+__global__ void __launch_bounds__(ScanBounds<EZ>::kThreads, ScanBounds<EZ>::kMinBlocks)
+scan_apply2_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
+                   ScanArgs a, const double* __restrict__ chunk_buf, const double* __restrict__ tile_start) {
+  constexpr int W = EZ::kMapDoubles, SW = EZ::kStateDoubles;
+  const DevProblem& P = probs[blockIdx.y];
+  const DevState& St = states[blockIdx.y];
+  const int M = P.M, CH = a.CH;
+  const ScanThread2 th(threadIdx.x, P.D, P.N, CH);
+  scan_tile_prefetch<EZ>(P, St, a, true);
+  extern __shared__ double sm[];                 // per family: [CH][cnt][SW] entering states | [CH][cnt][W] chunk maps
+  const long long nchunks = scan_num_chunks(a.nsteps);
+  const long long ntiles = scan_num_tiles(a.nsteps, CH);
+  const long long first = (long long)blockIdx.x * CH;
+  const int cnt = (int)((nchunks - first < CH) ? nchunks - first : CH);
+  double* s_state = sm + th.sm_off * (SW + W);
+  double* s_map = s_state + (size_t)CH * th.cnt * SW;
+  {
+    // every family stages its share of the tile's chunk aggregates (cnt * W contiguous doubles per chunk) with its own threads
+    const double* src = chunk_buf + (((size_t)blockIdx.y * nchunks + first) * M + th.n0) * W;
+    const int row = th.cnt * W;
+    for (int i = th.ftid; i < cnt * row; i += th.fthreads) {
+      const int j = i / row;
+      s_map[i] = src[(size_t)j * M * W + (i - j * row)];
+    }
+  }
+  __syncthreads();
+  if (th.live && th.c == 0) {
+    const double* tslot = tile_start + (((size_t)blockIdx.y * ntiles + blockIdx.x) * M + th.n) * SW;
+    if (th.fam_g) scan_apply_entry_thread<EG>(tslot, s_map, s_state, th.n - th.n0, th.cnt, cnt);
+    else scan_apply_entry_thread<EZ>(tslot, s_map, s_state, th.n - th.n0, th.cnt, cnt);
+  }
+  __syncthreads();
+  const long long chunk = first + th.c;
+  if (!th.live || chunk >= nchunks) return;
+  const double* sslot = s_state + ((size_t)th.c * th.cnt + (th.n - th.n0)) * SW;
+  if (th.fam_g) scan_apply_thread<EG>(P, St, a, th.n, chunk, sslot);
+  else scan_apply_thread<EZ>(P, St, a, th.n, chunk, sslot);
 }
 
 }  // namespace nsagp

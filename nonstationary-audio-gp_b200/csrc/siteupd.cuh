@@ -16,6 +16,14 @@
 //   phase D  all threads: rows back to HBM, coalesced.
 // ~110 registers, 16 warps per SM, no strided global access.  The per-point arithmetic is mom_point<FAST>'s, only the
 // sums over subbands are associated differently (four partial sums).
+//
+// PAIR (used whenever the link table exists): the four lanes of a step take the sigma points two at a time.  In the
+// single-point form all four lanes evaluate 1/v, 1/sqrt(v) and the Gaussian density of EVERY point -- 40 % of a lane's
+// FP64 work, done four times over.  Here lanes 0,1 finish point A and lanes 2,3 point B (the second shuffle round hands
+// each half the partial sums of its own point), the two halves swap the resulting coefficients (c1, c2), and the sums
+// that need only the density (Z, the modulators' g-sums) are kept per half and added once per step: the same number of
+// shuffles, 20 % fewer FP64 instructions.  The rows of W come from shared memory (broadcast reads) instead of 32
+// registers, which pays for the second point's coefficients.
 #pragma once
 #include "common.cuh"
 #include "fastmath.cuh"
@@ -39,10 +47,11 @@ __host__ __device__ inline int site4_smem_doubles(int M, int S, int ndist, bool 
   o += S + kNP * S;                                     // wn, xn
   o += ndist > 0 ? kSiteSteps * site_tab_stride(ndist) : 0;   // link table
   o += (kNP * S + 7) / 8;                               // index map (bytes)
+  o += 32 * kNP;                                        // W rows (PAIR form)
   return o;
 }
 
-template <int DPT, bool FULL>
+template <int DPT, bool FULL, bool PAIR>
 __global__ void __launch_bounds__(kSiteThreads, DPT == 4 ? 4 : 2)
 site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long k0, long long k1,
                     double alpha, double ep_damp, int write_lZ, int clamp_R) {
@@ -71,12 +80,15 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   double* s_xn = s_wn + S;
   double* s_tab = s_xn + kNP * S;                       // [step][kNP][nd][2] = (x, link(x))
   unsigned char* s_xi = reinterpret_cast<unsigned char*>(s_tab + (nd > 0 ? kSiteSteps * site_tab_stride(nd) : 0));
+  double* s_W = reinterpret_cast<double*>(s_xi) + (kNP * S + 7) / 8;     // [4 * DPT][kNP] (PAIR)
 
   // ---- phase A: rows in, cavities ------------------------------------------------------------------------------
   for (int i = tid; i < S; i += kSiteThreads) s_wn[i] = P.wn[i];
   for (int i = tid; i < kNP * S; i += kSiteThreads) s_xn[i] = P.xn[i];
   if (nd > 0)
     for (int i = tid; i < kNP * S; i += kSiteThreads) s_xi[i] = P.xidx[i];
+  if (PAIR)
+    for (int i = tid; i < 4 * DPT * kNP; i += kSiteThreads) s_W[i] = (i / kNP < D) ? P.W[i] : 0.0;
   if (tid < kSiteSteps) s_y[tid] = (tid < ns) ? St.y[kb + tid] : NAN;
   for (int i = tid; i < ns * M; i += kSiteThreads) {
     const int gi = i / M, n = i - gi * M;
@@ -107,13 +119,11 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   const double y = s_y[g];
   const bool valid = g < ns && !isnan(y);           // ihgp :398, gf_ep :237 (a missing sample is skipped)
   const int jj = dg < N ? dg : 0;
-  double W[DPT][kNP], muz[DPT], s2z[DPT];
+  double muz[DPT], s2z[DPT];
 #pragma unroll
   for (int i = 0; i < DPT; ++i) {
     const int d = dg + 4 * i;
     const bool in = d < D;
-#pragma unroll
-    for (int j = 0; j < kNP; ++j) W[i][j] = in ? P.W[d * kNP + j] : 0.0;
     muz[i] = (in && valid) ? s_mu[g * kSiteRow + d] : 0.0;
     s2z[i] = (in && valid) ? s_s2[g * kSiteRow + d] : 0.0;
   }
@@ -138,6 +148,108 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
 #pragma unroll
   for (int i = 0; i < DPT; ++i) { a1[i] = 0.0; a2[i] = 0.0; }
 
+  if constexpr (PAIR) {
+    // two points per round: lanes 0,1 of the step finish point A = s, lanes 2,3 point B = s + 1
+    const bool hi = (dg & 2) != 0;
+    const int j0 = dg & 1, j1 = j0 + 2;             // the modulators whose g-sums this lane keeps (for its half's points)
+    const bool has0 = j0 < N, has1 = j1 < N;
+    const double mu0 = (valid && has0) ? s_mu[g * kSiteRow + D + j0] : 0.0, rq0 = (valid && has0) ? s_rs2[g * kNP + j0] : 1.0;
+    const double mu1 = (valid && has1) ? s_mu[g * kSiteRow + D + j1] : 0.0, rq1 = (valid && has1) ? s_rs2[g * kNP + j1] : 1.0;
+    double ga1 = 0.0, ga2 = 0.0, gb1 = 0.0, gb2 = 0.0;
+    const double* Wr = s_W + dg * kNP;              // row d = dg + 4 i at Wr + 4 i kNP
+    auto links = [&](int s, double (&l)[kNP]) {
+#pragma unroll
+      for (int j = 0; j < kNP; ++j) l[j] = (j < N) ? tabg[(j * nd + s_xi[j * S + s]) * 2 + 1] : 0.0;
+    };
+    auto coeffs = [&](const double (&l)[kNP], double (&a)[DPT]) {
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) {
+        double ad = 0.0;
+#pragma unroll
+        for (int j = 0; j < kNP; ++j) ad = fma(l[j], Wr[(4 * i) * kNP + j], ad);
+        a[i] = ad;
+      }
+      if (P.lik_kind == 1) {
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) a[i] = sqrt_fast2(a[i]);
+      }
+    };
+    for (int s = 0; s < S; s += 2) {
+      const bool hasB = s + 1 < S;
+      double aA[DPT], aB[DPT];
+      {
+        double l[kNP];
+        links(s, l);
+        coeffs(l, aA);
+        links(hasB ? s + 1 : s, l);
+        coeffs(l, aB);
+      }
+      double vsA = 0.0, msA = 0.0, vsB = 0.0, msB = 0.0;
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) {
+        vsA = fma(aA[i] * aA[i], s2z[i], vsA);
+        msA = fma(aA[i], muz[i], msA);
+        vsB = fma(aB[i] * aB[i], s2z[i], vsB);
+        msB = fma(aB[i], muz[i], msB);
+      }
+      vsA += __shfl_xor_sync(0xffffffffu, vsA, 1);
+      msA += __shfl_xor_sync(0xffffffffu, msA, 1);
+      vsB += __shfl_xor_sync(0xffffffffu, vsB, 1);
+      msB += __shfl_xor_sync(0xffffffffu, msB, 1);
+      // second round: each half keeps its own point and receives the other half's partial of it
+      const double vs = (hi ? vsB : vsA) + __shfl_xor_sync(0xffffffffu, hi ? vsA : vsB, 2);
+      const double ms = (hi ? msB : msA) + __shfl_xor_sync(0xffffffffu, hi ? msA : msB, 2);
+      const int so = (hi && hasB) ? s + 1 : s;
+      const double v = noise + vs;
+      const double rv = rcp_fast2(v);
+      const double rsd = rsqrt_fast2(v);
+      const double res = yv - ms;
+      const double t = res * rsd;
+      const double pdf = exp_fast(-0.5 * (t * t)) * (rsd * kInvSqrt2Pi);
+      const double wp = ((hi && !hasB) ? 0.0 : s_wn[so]) * pdf;
+      const double q = res * rv;
+      const double c1 = wp * q;
+      const double c2 = wp * (q * q - rv);
+      const double c1o = __shfl_xor_sync(0xffffffffu, c1, 2);
+      const double c2o = __shfl_xor_sync(0xffffffffu, c2, 2);
+      const double c1A = hi ? c1o : c1, c1B = hi ? c1 : c1o;
+      const double c2A = hi ? c2o : c2, c2B = hi ? c2 : c2o;
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) {
+        a1[i] = fma(aA[i], c1A, a1[i]);
+        a1[i] = fma(aB[i], c1B, a1[i]);
+        a2[i] = fma(aA[i] * aA[i], c2A, a2[i]);
+        a2[i] = fma(aB[i] * aB[i], c2B, a2[i]);
+      }
+      Zs += wp;
+      if (has0) {
+        const double e = (tabg[(j0 * nd + s_xi[j0 * S + so]) * 2] - mu0) * rq0;
+        ga1 = fma(wp, e, ga1);
+        ga2 = fma(wp, e * e - rq0, ga2);
+      }
+      if (has1) {
+        const double e = (tabg[(j1 * nd + s_xi[j1 * S + so]) * 2] - mu1) * rq1;
+        gb1 = fma(wp, e, gb1);
+        gb2 = fma(wp, e * e - rq1, gb2);
+      }
+    }
+    // the two halves hold the sums over their own points
+    Zs += __shfl_xor_sync(0xffffffffu, Zs, 2);
+    ga1 += __shfl_xor_sync(0xffffffffu, ga1, 2);
+    ga2 += __shfl_xor_sync(0xffffffffu, ga2, 2);
+    gb1 += __shfl_xor_sync(0xffffffffu, gb1, 2);
+    gb2 += __shfl_xor_sync(0xffffffffu, gb2, 2);
+    g1 = hi ? gb1 : ga1;                            // lane dg updates modulator dg = j0 + 2 (dg >> 1)
+    g2 = hi ? gb2 : ga2;
+  } else {
+  double W[DPT][kNP];
+#pragma unroll
+  for (int i = 0; i < DPT; ++i) {
+    const int d = dg + 4 * i;
+    const bool in = d < D;
+#pragma unroll
+    for (int j = 0; j < kNP; ++j) W[i][j] = in ? P.W[d * kNP + j] : 0.0;
+  }
   double xq = 0.0, lq[kNP];
   auto fetch = [&](int s, double& x, double (&l)[kNP]) {
     if (nd > 0) {
@@ -202,6 +314,7 @@ site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
     const double e = (xj - mug) * rs2g;
     g1 = fma(wp, e, g1);
     g2 = fma(wp, e * e - rs2g, g2);
+  }
   }
 
   // ---- phase C: moments -> damped Power-EP update of the sites this lane holds -----------------------------------

@@ -257,13 +257,15 @@ def test_c2_bench_schedule_prefix_against_oracle(nsagp, gpu_lib):
 
 
 # ------------------------------------------------------------------------------------------ family-specialised scans
-@pytest.fixture
-def family_scans(nsagp):
-    """Force the per-family form of the frozen-site scans (default: only signals of >= 400 000 steps)."""
+@pytest.fixture(params=[1, 0], ids=["one-tile", "launch-per-family"])
+def family_scans(nsagp, request):
+    """The family-specialised form of the frozen-site scans both as one CTA tile for the two families (default) and as
+    one launch per family."""
     L = nsagp._lib
     L.check(L.lib().nsagp_scan_config(0))
+    L.check(L.lib().nsagp_scan_merge(request.param))
     yield
-    L.check(L.lib().nsagp_scan_config(400000))
+    L.check(L.lib().nsagp_scan_merge(1))
 
 
 @pytest.mark.parametrize("D,N,k1,k2", [(16, 3, "exp", "matern52"),        # (BM, bz, bg) = (3, 2, 3): C2 / C3
@@ -288,3 +290,37 @@ def test_family_specialised_scans_match_oracle(nsagp, gpu_lib, family_scans, ent
     assert rel_err(og["nlZ"], oo["nlZ"]) < TOL_SCAN and rel_err(og["MS"], oo["MS"]) < TOL_SCAN
     assert rel_err(og["ttau"], oo["ttau"]) < TOL_SCAN and rel_err(og["MF"], oo["MF"]) < TOL_SCAN
     assert og["n_negcav"] == oo["n_negcav"]
+
+
+# ------------------------------------------------------------------------------------------ site-update forms
+@pytest.mark.parametrize("entry_name", ["ihgp", "gfep"])
+@pytest.mark.parametrize("D,N,p", [(16, 3, 9), (6, 2, 9), (20, 4, 7), (5, 2, 3)])
+def test_site_update_forms_agree(nsagp, gpu_lib, entry_name, D, N, p):
+    """The smoother-side site update in its three forms (csrc/siteupd.cuh: sigma points two at a time / one at a time;
+    csrc/ihgp.cuh: one thread per step) against the oracle and against each other: D > 16 (eight subbands per lane),
+    N = 2 .. 4 (every split of the modulators' g-sums over the four lanes), S = 5 .. 97 (always odd: the last round has
+    one point), gaps."""
+    from oracle import gf_ep, ihgp_ep
+    T = 200
+    pb = make_problem(nsagp, D, N, T, "exp", "matern52", seed=300 + D, kind="precalc", p=p, shift=1.0, gaps=True)
+    damping = np.linspace(0.4, 0.2, 3)
+    if entry_name == "ihgp":
+        ref, got = ihgp_ep.ihgp_ep_modulator_nmf, nsagp.ihgp_ep_modulator_nmf
+    else:
+        ref, got = gf_ep.gf_ep_modulator_nmf, nsagp.gf_ep_modulator_nmf
+    Eo, Vo, _, _, _, oo = ref(*_args(pb, "ref", pb["t"], 0.75, damping, 3))
+    L = nsagp._lib
+    res = {}
+    try:
+        for form in (0, 2, 1):
+            L.check(L.lib().nsagp_site_config(form))
+            Eg, Vg, _, _, _, og = got(*_args(pb, "gpu", pb["t"], 0.75, damping, 3))
+            res[form] = (Eg, og["ttau"], og["tnu"], og["nlZ"])
+            assert rel_err(Eg, Eo) < TOL_SCAN and rel_err(Vg, Vo) < TOL_SCAN, form
+            assert rel_err(og["ttau"], oo["ttau"]) < TOL_SCAN and rel_err(og["nlZ"], oo["nlZ"]) < TOL_SCAN, form
+            assert og["n_negcav"] == oo["n_negcav"], form
+    finally:
+        L.check(L.lib().nsagp_site_config(0))
+    for form in (2, 1):
+        for a, b in zip(res[0], res[form]):
+            assert rel_err(a, b) < 1e-9, form

@@ -96,8 +96,24 @@ def test_giekf_gradient_nan_and_limits(nsagp, gpu_lib):
     y = pb["y"].copy(); y[7] = np.nan                      # a missing sample makes the reference's energy NaN
     e, g = nsagp.gf_giekf_modulator_nmf(pb["w"], pb["t"], y, pb["ss_gpu"], None, None, k1, k2, 1, D, N, 1, 1, GradObj="on")
     assert np.isnan(e) and np.all(np.isnan(g)) and g.size == 1 + 3 * D + 2 * N
-    # n = 137 (32 matern32 subbands): 2 n^2 doubles do not fit one CTA's shared memory -> a clear error, not a fallback
-    pb = make_problem(nsagp, 32, 3, 50, "matern32", "matern52", seed=9, w_lik=1e-2)
-    with pytest.raises(nsagp._lib.NsagpError, match="too large"):
-        nsagp.gf_giekf_modulator_nmf(pb["w"], pb["t"], pb["y"], pb["ss_gpu"], None, None, "matern32", "matern52", 1, 32, 3, 1, 1,
-                                     GradObj="on")
+
+
+def test_giekf_gradient_c4_matern32_shape_matches_oracle(nsagp, gpu_lib):
+    """C4's other shape: D = 32 matern32 subbands, N = 3 matern52 modulators (n = 137, 103 parameters).  2 n^2 doubles
+    do not fit one CTA's shared memory, so dP_j lives in an HBM scratch (csrc/ekfgrad.cuh: dP_hbm) -- same code path
+    otherwise; checked entry by entry against the oracle's dense recursion on a short signal."""
+    from oracle import giekf
+    D, N, T, k1, k2 = 32, 3, 25, "matern32", "matern52"
+    pb = make_problem(nsagp, D, N, T, k1, k2, seed=9, w_lik=1e-2)
+    eo, go = giekf.gf_giekf_modulator_nmf(pb["w"], pb["t"], pb["y"], _ss_ref_with_derivs(), None, None, k1, k2, 1, D, N, 1, 1,
+                                          GradObj="on")
+    eg, gg = nsagp.gf_giekf_modulator_nmf(pb["w"], pb["t"], pb["y"], pb["ss_gpu"], None, None, k1, k2, 1, D, N, 1, 1,
+                                          GradObj="on")
+    assert gg.shape == go.shape == (103,)
+    assert abs(eg - eo) < TOL * abs(eo)
+    assert np.all(np.abs(gg - go) <= TOL * np.abs(go) + 1e-300), np.c_[gg, go]
+    # a longer signal runs and agrees with the energy-only call
+    pb = make_problem(nsagp, D, N, 1500, k1, k2, seed=10, w_lik=1e-2)
+    e, g = nsagp.gf_giekf_modulator_nmf(pb["w"], pb["t"], pb["y"], pb["ss_gpu"], None, None, k1, k2, 1, D, N, 1, 1, GradObj="on")
+    e_off, _ = nsagp.gf_giekf_modulator_nmf(pb["w"], pb["t"], pb["y"], pb["ss_gpu"], None, None, k1, k2, 1, D, N, 1, 1)
+    assert np.all(np.isfinite(g)) and abs(e - e_off) < 1e-10 * abs(e)
