@@ -314,6 +314,10 @@ int nsagp_scan_merge(int32_t on);
 /* 1 (default) = every CTA tile of a scan starts by bulk-prefetching its input rows into L2 (cp.async.bulk.prefetch.L2);
  * 0 = off.  No effect on results. */
 int nsagp_scan_prefetch(int32_t on);
+/* Geometry of a CTA tile of the scans: at most max_chunks 32-step chunks (1..16, default 16) and at most max_threads
+ * threads (256, the default: 128 registers per thread at two tiles per SM, hardly any spills; or 320: 96 registers,
+ * more warps).  No effect on results beyond the association of the tile aggregates (rounding). */
+int nsagp_scan_tile(int32_t max_chunks, int32_t max_threads);
 /* Form of the smoother-side site update (csrc/siteupd.cuh): 0 (default) = four lanes per time step, sigma points two at
  * a time when the rule has few distinct coordinates (every utp_ws rule), else one at a time; 2 = always one at a time;
  * 1 = the first-generation kernel, one thread per step (csrc/ihgp.cuh).  The environment variable NSAGP_SITE_FORM sets

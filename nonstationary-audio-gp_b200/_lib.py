@@ -140,6 +140,7 @@ def lib():
     L.nsagp_scan_config.argtypes = [C.c_int64]
     L.nsagp_scan_merge.argtypes = [C.c_int32]
     L.nsagp_scan_prefetch.argtypes = [C.c_int32]
+    L.nsagp_scan_tile.argtypes = [C.c_int32, C.c_int32]
     L.nsagp_site_config.argtypes = [C.c_int32]
     L.nsagp_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64]
     L.nsagp_comm_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
@@ -161,7 +162,7 @@ EXPORTS = ["nsagp_version", "nsagp_last_error", "nsagp_set_device", "nsagp_set_s
            "nsagp_plan_set_adf_form", "nsagp_fastmath_eval", "nsagp_release_cache", "nsagp_giekf", "nsagp_plan_set_range",
            "nsagp_plan_stage", "nsagp_ihgp_tables", "nsagp_giekf_config", "nsagp_giekf_timings", "nsagp_giekf_carry", "nsagp_mc_reconstruct",
            "nsagp_comm_create", "nsagp_comm_export", "nsagp_comm_connect", "nsagp_comm_destroy", "nsagp_plan_comm_slot_doubles",
-           "nsagp_plan_run_chunked", "nsagp_plan_set_adf_parallel", "nsagp_plan_adf_mismatch", "nsagp_fastfb", "nsagp_scan_config", "nsagp_scan_merge", "nsagp_scan_prefetch", "nsagp_site_config", "nsagp_giekf_grad"]
+           "nsagp_plan_run_chunked", "nsagp_plan_set_adf_parallel", "nsagp_plan_adf_mismatch", "nsagp_fastfb", "nsagp_scan_config", "nsagp_scan_merge", "nsagp_scan_prefetch", "nsagp_scan_tile", "nsagp_site_config", "nsagp_giekf_grad"]
 
 
 def check(status):

@@ -685,7 +685,14 @@ int nsagp_site_config(int32_t form) {
   return NSAGP_OK;
 }
 
-int g_scan_merge = 1, g_scan_l2pf = 1;
+int g_scan_merge = 1, g_scan_l2pf = 1, g_scan_ch_max = 16, g_scan_threads2 = 256;
+int nsagp_scan_tile(int32_t max_chunks, int32_t max_threads) {
+  if (max_chunks < 1 || max_chunks > 16) return fail(NSAGP_ERR_INVALID, "max_chunks must be in 1..16");
+  if (max_threads != 320 && max_threads != 256) return fail(NSAGP_ERR_INVALID, "max_threads must be 320 or 256");
+  g_scan_ch_max = max_chunks;
+  g_scan_threads2 = max_threads;
+  return NSAGP_OK;
+}
 int nsagp_scan_merge(int32_t on) {
   g_scan_merge = on ? 1 : 0;
   return NSAGP_OK;
@@ -917,7 +924,7 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
 // by the shared memory the tile needs for its chunk aggregates.
 int scan_ch(const nsagp_plan* pl, int map_doubles, int max_threads, int lat) {
   const size_t per_chunk = (size_t)pl->M * map_doubles * sizeof(double);
-  int ch = std::min(16, std::max(1, max_threads / lat));     // (latent, chunk) threads of a CTA tile
+  int ch = std::min(g_scan_ch_max, std::max(1, max_threads / lat));     // (latent, chunk) threads of a CTA tile
   while (ch > 1 && per_chunk * ch > 80 * 1024) --ch;         // phase 3 stages maps + states: < 2x this
   return ch;
 }
@@ -948,6 +955,16 @@ template <class EZ_, class EG_> struct ElemPair { using EZ = EZ_; using EG = EG_
 // Distinct element types per family: one CTA tile runs both (scan_reduce2 / scan_apply2_kernel, whole warps per family);
 // nsagp_scan_merge(0) launches each family on its own instead (the form measured in profiles/r2i_*, kept for comparison).
 static bool scan_merge() { return g_scan_merge != 0; }
+// thread bound of the merged tile (scan.cuh: TH)
+template <class Pair> static int scan2_bound() {
+  return (ScanBounds<typename Pair::EZ>::kThreads == kScanThreads2 && g_scan_threads2 == 256) ? 256 : ScanBounds<typename Pair::EZ>::kThreads;
+}
+template <class Pair> static auto scan2_reduce_fn() {
+  return scan2_bound<Pair>() == 256 ? scan_reduce2_kernel<typename Pair::EZ, typename Pair::EG, 256> : scan_reduce2_kernel<typename Pair::EZ, typename Pair::EG>;
+}
+template <class Pair> static auto scan2_apply_fn() {
+  return scan2_bound<Pair>() == 256 ? scan_apply2_kernel<typename Pair::EZ, typename Pair::EG, 256> : scan_apply2_kernel<typename Pair::EZ, typename Pair::EG>;
+}
 
 template <class Pair>
 int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, int dir, int init, long long kinit, int flags) {
@@ -955,7 +972,7 @@ int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, 
   a.flags = flags | (g_scan_l2pf ? kScanFlagL2Prefetch : 0);
   constexpr bool same = std::is_same<typename Pair::EZ, typename Pair::EG>::value;
   const bool merge = !same && scan_merge();
-  const int maxthr = ScanBounds<typename Pair::EZ>::kThreads;
+  const int maxthr = merge ? scan2_bound<Pair>() : ScanBounds<typename Pair::EZ>::kThreads;
   a.CH = scan_ch(pl, Pair::EZ::kMapDoubles, maxthr, same || merge ? pl->M : std::max(pl->D, pl->N));
   while (merge && a.CH > 1 && scan2_threads(pl->D, pl->N, a.CH) > maxthr) --a.CH;
   // a CTA tile of (family latents)*CH threads must fit an SM (registers, shared memory): ask the occupancy calculator
@@ -976,8 +993,7 @@ int scan_setup(nsagp_plan* pl, ScanArgs& a, long long kfirst, long long nsteps, 
       return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->M, pl->M * ch);
     } else {
       if (merge)
-        return ok(scan_reduce2_kernel<typename Pair::EZ, typename Pair::EG>, scan_apply2_kernel<typename Pair::EZ, typename Pair::EG>,
-                  pl->M, scan2_threads(pl->D, pl->N, ch));
+        return ok(scan2_reduce_fn<Pair>(), scan2_apply_fn<Pair>(), pl->M, scan2_threads(pl->D, pl->N, ch));
       return ok(scan_reduce_kernel<typename Pair::EZ>, scan_apply_kernel<typename Pair::EZ>, pl->D, pl->D * ch) &&
              ok(scan_reduce_kernel<typename Pair::EG>, scan_apply_kernel<typename Pair::EG>, pl->N, pl->N * ch);
     }
@@ -1003,7 +1019,7 @@ int scan_reduce(nsagp_plan* pl, const ScanArgs& a, double* agg_host) {
   if constexpr (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
     if ((rcl = launch(scan_reduce_kernel<typename Pair::EZ>, 0, pl->M))) return rcl;
   } else if (scan_merge()) {
-    auto kern = scan_reduce2_kernel<typename Pair::EZ, typename Pair::EG>;
+    auto kern = scan2_reduce_fn<Pair>();
     const size_t sm1 = (size_t)a.CH * pl->M * Pair::EZ::kMapDoubles * sizeof(double);
     if (sm1 > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
     kern<<<grid, scan2_threads(pl->D, pl->N, a.CH), sm1, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_tile);
@@ -1076,7 +1092,7 @@ int scan_finish(nsagp_plan* pl, ScanArgs a, const double* prev_host, int nprev, 
     if constexpr (std::is_same<typename Pair::EZ, typename Pair::EG>::value) {
       if ((rcl = launch(scan_apply_kernel<typename Pair::EZ>, 0, pl->M))) return rcl;
     } else if (scan_merge()) {
-      auto kern = scan_apply2_kernel<typename Pair::EZ, typename Pair::EG>;
+      auto kern = scan2_apply_fn<Pair>();
       const size_t sm3 = (size_t)a.CH * pl->M * (Pair::EZ::kStateDoubles + Pair::EZ::kMapDoubles) * sizeof(double);
       if (sm3 > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
       kern<<<grid, scan2_threads(pl->D, pl->N, a.CH), sm3, g_stream>>>(pl->d_probs, pl->d_states, a, pl->d_chunk, pl->d_start);

@@ -212,8 +212,13 @@ struct ScanThread2 {
 };
 __host__ __device__ inline int scan2_threads(int D, int N, int CH) { return ((CH * D + 31) & ~31) + CH * N; }
 
-template <class EZ, class EG>
-__global__ void __launch_bounds__(ScanBounds<EZ>::kThreads, ScanBounds<EZ>::kMinBlocks)
+// TH: thread bound of the CTA tile.  The mean elements ask for two tiles per SM; with TH = 320 (16 chunks: 304 threads) that
+// caps a thread at 96 registers and the walks spill 250-750 bytes, with TH = 256 (12 chunks: 228 threads) at 128 registers
+// and the spills all but vanish -- fewer warps per SM against less local-memory traffic through an L1 that is the
+// busiest unit of these kernels (profiles/r2n_scan.md).  Measured (profiles/r2q_ab.jsonl): 256 threads are 6-26 % faster at
+// every length; the host picks them by default (nsagp_scan_tile).
+template <class EZ, class EG, int TH = ScanBounds<EZ>::kThreads>
+__global__ void __launch_bounds__(TH, ScanBounds<EZ>::kMinBlocks)
 scan_reduce2_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
                     ScanArgs a, double* __restrict__ chunk_buf, double* __restrict__ tile_buf) {
   constexpr int W = EZ::kMapDoubles;
@@ -449,8 +454,8 @@ scan_apply_kernel(const DevProblem* __restrict__ probs, const DevState* __restri
   scan_apply_thread<Elem>(P, St, a, n, chunk, s_state + ((size_t)c * cnt_lat + (n - n0)) * SW);
 }
 
-template <class EZ, class EG>
-__global__ void __launch_bounds__(ScanBounds<EZ>::kThreads, ScanBounds<EZ>::kMinBlocks)
+template <class EZ, class EG, int TH = ScanBounds<EZ>::kThreads>
+__global__ void __launch_bounds__(TH, ScanBounds<EZ>::kMinBlocks)
 scan_apply2_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states,
                    ScanArgs a, const double* __restrict__ chunk_buf, const double* __restrict__ tile_start) {
   constexpr int W = EZ::kMapDoubles, SW = EZ::kStateDoubles;

@@ -21,19 +21,18 @@ lib = L.lib()
 itts = 4
 wn, xn = nsagp.utp_ws(bench.P_CUB, bench.N)
 mom = nsagp.likModulatorPreCalcwn(nsagp.Softplus(bench.SHIFT), wn, xn)
-CONFIGS = [  # name, merge, family_min_steps, site form, L2 prefetch
-    ("r2i: launch per family >= 400k, site 1pt", 0, 400000, 2, 0),
-    ("launch per family >= 400k, site 2pt", 0, 400000, 0, 0),
-    ("one tile always, site 2pt", 1, 0, 0, 0),
-    ("one tile always, site 2pt, L2 prefetch", 1, 0, 0, 1),
-    ("padded always, site 2pt, L2 prefetch", 1, 1 << 40, 0, 1),
+CONFIGS = [  # name, merge, family_min_steps, site form, L2 prefetch, chunks per tile, tile threads, (unused)
+    ("r2i: launch per family >= 400k, site 1pt", 0, 400000, 2, 0, 16, 320, 0),
+    ("one tile, site 2pt, L2 prefetch, 320 threads", 1, 0, 0, 1, 16, 320, 0),
+    ("  same, 256 threads (128 registers): default", 1, 0, 0, 1, 16, 256, 0),
+    ("  same, 256 threads, 8 chunks", 1, 0, 0, 1, 8, 256, 0),
 ]
 for kind, T in ((L.KIND_IHGP, 100000), (L.KIND_IHGP, 2000000), (L.KIND_IHGP, 10000000), (L.KIND_FULL, 500000)):
     hyp, y = bench.make_signal(nsagp, 0, T)
     mdl, tabs = bench.host_setup(nsagp, hyp)
-    for name, merge, fam, form, pf in CONFIGS:
+    for name, merge, fam, form, pf, ch, th, el in CONFIGS:
         L.check(lib.nsagp_scan_merge(merge)); L.check(lib.nsagp_scan_config(fam)); L.check(lib.nsagp_site_config(form))
-        L.check(lib.nsagp_scan_prefetch(pf))
+        L.check(lib.nsagp_scan_prefetch(pf)); L.check(lib.nsagp_scan_tile(ch, th))
         with nsagp.Plan(kind, [mdl], [(mom, np.log([hyp.w_lik]), hyp.W)], bench.ALPHA, bench.damping(itts), itts, y[None, :],
                         L.MODE_PREDICT, tables=[tabs] if kind == L.KIND_IHGP else None) as plan:
             if T > 100000:
@@ -50,4 +49,4 @@ for kind, T in ((L.KIND_IHGP, 100000), (L.KIND_IHGP, 2000000), (L.KIND_IHGP, 100
         print(json.dumps(dict(kind="ihgp" if kind == L.KIND_IHGP else "full", T=T, config=name,
                               filter_ms_per_1e6=per("fixed_filter", itts - 1), smoother_ms_per_1e6=per("smoother", itts),
                               site_ms_per_1e6=per("site_update", itts - 1), nlZ=nlZ)), flush=True)
-L.check(lib.nsagp_scan_merge(1)); L.check(lib.nsagp_scan_config(0)); L.check(lib.nsagp_site_config(0)); L.check(lib.nsagp_scan_prefetch(1))
+L.check(lib.nsagp_scan_merge(1)); L.check(lib.nsagp_scan_config(0)); L.check(lib.nsagp_site_config(0)); L.check(lib.nsagp_scan_prefetch(1)); L.check(lib.nsagp_scan_tile(16, 256))

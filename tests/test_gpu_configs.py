@@ -20,6 +20,7 @@ from conftest import make_problem, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL_SEQ, TOL_SCAN = 1e-8, 1e-6
+SCAN_TILE_DEFAULT = (16, 256)      # the library's default (csrc/api.cu)
 
 
 def _args(pb, which, xt, alpha, damping, itts):
@@ -324,3 +325,28 @@ def test_site_update_forms_agree(nsagp, gpu_lib, entry_name, D, N, p):
     for form in (2, 1):
         for a, b in zip(res[0], res[form]):
             assert rel_err(a, b) < 1e-9, form
+
+
+# ------------------------------------------------------------------------------------------ scan tile geometry / element forms
+@pytest.mark.parametrize("D,N,k1,k2", [(16, 3, "exp", "matern52"),        # (3, 2, 3): C2
+                                        (5, 2, "matern32", "matern52"),    # (4, 4, 3)
+                                        (4, 2, "exp", "exp")])             # no specialised pair: padded path
+@pytest.mark.parametrize("threads,chunks", [(256, 16), (320, 16), (256, 5), (320, 3)])
+def test_scan_tile_geometry_matches_oracle(nsagp, gpu_lib, threads, chunks, D, N, k1, k2):
+    """The frozen-site scans of the infinite-horizon path with every tile geometry (nsagp_scan_tile: 256-thread tiles at
+    128 registers / 320-thread tiles at 96, full and short tiles) against the oracle."""
+    from oracle import ihgp_ep
+    T = 1500 if chunks == 16 else 700                # several tiles, a ragged last tile
+    pb = make_problem(nsagp, D, N, T, k1, k2, seed=120 + D, kind="precalc", p=9, shift=1.0, gaps=True)
+    damping = np.linspace(0.4, 0.2, 3)
+    Eo, Vo, _, _, _, oo = ihgp_ep.ihgp_ep_modulator_nmf(*_args(pb, "ref", pb["t"], 0.75, damping, 3))
+    L = nsagp._lib
+    try:
+        L.check(L.lib().nsagp_scan_tile(chunks, threads))
+        Eg, Vg, _, _, _, og = nsagp.ihgp_ep_modulator_nmf(*_args(pb, "gpu", pb["t"], 0.75, damping, 3))
+    finally:
+        L.check(L.lib().nsagp_scan_tile(*SCAN_TILE_DEFAULT))
+    assert rel_err(Eg, Eo) < TOL_SCAN and rel_err(Vg, Vo) < TOL_SCAN
+    assert rel_err(og["nlZ"], oo["nlZ"]) < TOL_SCAN and rel_err(og["MS"], oo["MS"]) < TOL_SCAN
+    assert rel_err(og["ttau"], oo["ttau"]) < TOL_SCAN and rel_err(og["MF"], oo["MF"]) < TOL_SCAN
+    assert og["n_negcav"] == oo["n_negcav"]
