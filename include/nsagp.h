@@ -148,7 +148,8 @@ int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_f
 
 /* Test hook: the straight-line FP64 routines used on the critical path of the
  * sequential passes (csrc/fastmath.cuh), evaluated for n host values.
- * op: 0 1/x, 1 1/sqrt(x), 2 sqrt(x), 3 exp(x), 4 log(x) for x >= 1, 5 log(1+exp(x)). */
+ * op: 0 1/x, 1 1/sqrt(x), 2 sqrt(x), 3 exp(x), 4 log(x) for x >= 1, 5 log(1+exp(x)), 6-8 the variants of 0-2 with
+ * one Newton step fewer, 9 the table-driven log(x) for x >= 1, 10 log(1+exp(x)) built on it (finite x). */
 int nsagp_fastmath_eval(int32_t op, int64_t n, const double* x, double* out);
 
 /* Steady-state tables of the infinite-horizon path built natively on the host

@@ -23,7 +23,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("NSAGP_LIB") or os.path.join(CSRC, "libnsagp.so")
 _SOURCES = ["api.cu", "api_full.inc", "common.cuh", "mom.cuh", "momcta.cuh", "mombatch.cuh", "lookup.cuh", "ihgp.cuh",
             "gfep.cuh", "adfcta.cuh", "fastmath.cuh", "scan.cuh", "ekf.cuh", "ekfscan.cuh", "mcrec.cuh", "api_mc.inc", "api_ekf.inc", "api_chunk.inc", "api_tables.inc", "comm.cuh",
-            "api_comm.inc", "siteupd.cuh", "ekfbig.cuh", "fastfb.cuh", "api_fb.inc", "ekfgrad.cuh"]
+            "api_comm.inc", "siteupd.cuh", "ekfbig.cuh", "fastfb.cuh", "api_fb.inc", "ekfgrad.cuh", "logtab.inc"]
 
 c_double_p = C.POINTER(C.c_double)
 

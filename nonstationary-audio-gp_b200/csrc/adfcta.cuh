@@ -70,9 +70,10 @@ __device__ __forceinline__ int lookup_by_ttau(const double* cthr, int nr, double
 
 // Shared-memory layout (doubles) of the CTA kernels.
 struct AdfSmem {
-  int mom, wn, xn, q, cthr, hph, wtab, sdt, rs2t, total;
+  int logtab, mom, wn, xn, q, cthr, hph, wtab, sdt, rs2t, total;
   __host__ __device__ AdfSmem(int nmw, int NVP, int S, int M, int N, int nr, int BM, bool tables, bool fullstate) {
     int o = 0;
+    logtab = o; o += kLogTabDoubles;                   // fastmath.cuh: log_ge1_tab (first: 16-byte aligned)
     mom = o; o += 72 + nmw * 4 * NVP;
     wn = o; o += S;
     xn = o; o += kNP * S;
@@ -135,9 +136,10 @@ __global__ void adf_mismatch_kernel(const DevProblem* __restrict__ probs, const 
 template <int DPT, bool SINGLE>
 __device__ __forceinline__ void adf_moment_loop(const MomParams& mp, const double* __restrict__ yv, long long T,
                                                 long long k0, long long k1, int mom_all, bool skip_nan,
-                                                double* s_mom, int mtid, int nmt, int nthreads) {
+                                                double* s_mom, const double* s_logtab, int mtid, int nmt, int nthreads) {
   MomCtaThread<DPT> th;
   th.init(mp, mtid);
+  th.ltab = (unsigned)__cvta_generic_to_shared(s_logtab);
   const double noise = mp.sn2;                        // alpha = 1 in the filter (:256 / :144)
   double* s_part = s_mom + MomCta<DPT>::kCav;
   double y_nx = yv[k0];
@@ -178,6 +180,7 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   double* s_xn = sm + L.xn;
   for (int i = tid; i < P.S; i += nthreads) s_wn[i] = P.wn[i];
   for (int i = tid; i < kNP * P.S; i += nthreads) s_xn[i] = P.xn[i];
+  log_tab_fill(sm + L.logtab, tid, nthreads);
   // steady-state tables: shared memory when they fit (TABS), else straight from HBM/L2
   const double* cthr = TABS ? sm + L.cthr + kCthrPad : P.cthr;
   const double* hphtab = TABS ? sm + L.hph : P.HPHtab;
@@ -194,7 +197,7 @@ ihgp_adf_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __rest
   const MomParams mp = make_mom_params(P, P.W, s_wn, s_xn);
 
   if (tid >= 32) {
-    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, k1, mom_all, true, s_mom, tid - 32, nmt, nthreads);
+    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, k1, mom_all, true, s_mom, sm + L.logtab, tid - 32, nmt, nthreads);
     return;
   }
 
@@ -390,11 +393,12 @@ gfep_filter_cta_kernel(const DevProblem* __restrict__ probs, const DevState* __r
   for (int i = tid; i < P_.S; i += nthreads) s_wn[i] = P_.wn[i];
   for (int i = tid; i < kNP * P_.S; i += nthreads) s_xn[i] = P_.xn[i];
   for (int i = tid; i < M * BM * BM; i += nthreads) s_q[i] = P_.Q[i];
+  log_tab_fill(sm + L.logtab, tid, nthreads);
   __syncthreads();
   const MomParams mp = make_mom_params(P_, P_.W, s_wn, s_xn);
 
   if (tid >= 32) {
-    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, k1, mom_all, true, s_mom, tid - 32, nmt, nthreads);
+    adf_moment_loop<DPT, SINGLE>(mp, St.y, T, k0, k1, mom_all, true, s_mom, sm + L.logtab, tid - 32, nmt, nthreads);
     return;
   }
 

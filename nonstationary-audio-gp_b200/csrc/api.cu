@@ -364,6 +364,9 @@ int nsagp_mom_batch_warp(const nsagp_lik* lik, int32_t D, int32_t N, double ep_f
 
 namespace {
 __global__ void fastmath_kernel(int op, long long n, const double* __restrict__ x, double* __restrict__ out) {
+  __shared__ __align__(16) double s_logtab[kLogTabDoubles];
+  log_tab_fill(s_logtab, threadIdx.x, blockDim.x);
+  __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
@@ -377,7 +380,9 @@ __global__ void fastmath_kernel(int op, long long n, const double* __restrict__ 
     case 5: r = softplus_fast(v); break;
     case 6: r = rcp_fast2(v); break;
     case 7: r = rsqrt_fast2(v); break;
-    default: r = sqrt_fast2(v); break;
+    case 8: r = sqrt_fast2(v); break;
+    case 9: r = log_ge1_tab(v, (unsigned)__cvta_generic_to_shared(s_logtab)); break;
+    default: r = softplus_tab_finite(v, (unsigned)__cvta_generic_to_shared(s_logtab)); break;
   }
   out[i] = r;
 }
@@ -386,7 +391,7 @@ __global__ void fastmath_kernel(int op, long long n, const double* __restrict__ 
 extern "C" {
 
 int nsagp_fastmath_eval(int32_t op, int64_t n, const double* x, double* out) {
-  if (op < 0 || op > 8 || n < 0 || !x || !out) return fail(NSAGP_ERR_INVALID, "bad argument");
+  if (op < 0 || op > 10 || n < 0 || !x || !out) return fail(NSAGP_ERR_INVALID, "bad argument");
   if (n == 0) return NSAGP_OK;
   int rc = ensure_stream();
   if (rc) return rc;

@@ -147,6 +147,45 @@ __device__ __forceinline__ double log_ge1_fast_t(double u) {
 }
 __device__ __forceinline__ double log_ge1_fast(double u) { return log_ge1_fast_t<true>(u); }
 
+// log(u) for finite normal u >= 1 WITHOUT the division of the scheme above: u = 2^k m, the top seven mantissa bits
+// j select c_j = 1 + j/128, r = m * fl(1/c_j) - 1 in [0, 2^-7) (one FMA; the rounding of 1/c_j is folded into the
+// tabulated -log(fl(1/c_j))), log(m) = log1p(r) - log(fl(1/c_j)) with a degree-8 Taylor polynomial (truncation r^9/9 <=
+// 2^-66).  c_0 = 1 and its table entry is exactly 0, so results near 0 keep their relative accuracy.  Dependent chain:
+// ~100 cycles against ~200 (the reciprocal alone is ~70); <= 1.3 ulp (tests/test_gpu_mom.py).  The table (2 KB) must
+// be in shared memory (log_tab_fill) -- the lanes of a warp read different rows.
+__device__ const double kLogTab[256] = {
+#include "logtab.inc"
+};
+constexpr int kLogTabDoubles = 256;
+
+__device__ __forceinline__ void log_tab_fill(double* s_tab, int tid, int nthreads) {
+  for (int i = tid; i < kLogTabDoubles; i += nthreads) s_tab[i] = kLogTab[i];
+}
+
+// tab_saddr: shared-memory BYTE address of the table (16-byte aligned)
+__device__ __forceinline__ double log_ge1_tab(double u, unsigned tab_saddr) {
+  const int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  const int k = (hi >> 20) - 1023;
+  const unsigned j = ((unsigned)hi >> 13) & 127u;
+  double ic, lc;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ic), "=d"(lc) : "r"(tab_saddr + 16u * j));
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double dk = (double)k;
+  const double r = fma(m, ic, -1.0);
+  const double A = fma(dk, 6.93147180369123816490e-01, lc);
+  const double r2 = r * r;
+  const double b1 = fma(r, (1.0 / 3.0), -0.5);
+  const double b2 = fma(r, 0.2, -0.25);
+  const double b3 = fma(r, (1.0 / 7.0), -(1.0 / 6.0));
+  const double r4 = r2 * r2;
+  const double q01 = fma(r2, b2, b1);
+  const double q23 = fma(r2, -0.125, b3);
+  const double q = fma(r4, q23, q01);
+  const double B = fma(dk, 1.90821492927058770002e-10, fma(r2, q, r));
+  return A + B;
+}
+
 // The reference's link, literally log(1 + exp(g - shift)) (likModulatorNMFPower.m:44 with
 // link = @(g) log(1+exp(g-c))): the rounding of 1 + exp(.) is part of the arithmetic.
 __device__ __forceinline__ double softplus_fast(double xs) {
@@ -155,6 +194,11 @@ __device__ __forceinline__ double softplus_fast(double xs) {
 // For finite arguments only (no NaN propagation): the moment warps of the sequential passes.
 __device__ __forceinline__ double softplus_fast_finite(double xs) {
   return log_ge1_fast_t<false>(1.0 + exp_fast_t<false>(xs));
+}
+
+// The same with the table-driven logarithm (the moment warps of the CTA kernels: the link is the head of their chain).
+__device__ __forceinline__ double softplus_tab_finite(double xs, unsigned tab_saddr) {
+  return log_ge1_tab(1.0 + exp_fast_t<false>(xs), tab_saddr);
 }
 
 // sqrt(x) for finite normal x > 0 (no zero handling).

@@ -58,6 +58,7 @@ struct MomCtaThread {
   double W[DPT][kNP];     // rows dg, dg+4, ... of W
   double xn0, wn0;        // SINGLE: this thread's abscissa (modulator jj) and weight (0 if inactive)
   int dg, jj;
+  unsigned ltab = 0;      // shared-memory byte address of the logarithm table (fastmath.cuh: log_ge1_tab)
   __device__ __forceinline__ void init(const MomParams& p, int mtid) {
     dg = mtid & 3;
     jj = dg < p.N ? dg : 0;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void mom_cta_points(const MomParams& p, const MomCtaT
     const double xi = SINGLE ? th.xn0 : p.xn[jj * p.S + s];
     const double xj = fma(sdg, xi, mug);
     // lanes dg >= N repeat modulator 0; their value meets the zero-padded column of W
-    const double lj = softplus_fast_finite(xj - p.shift);
+    const double lj = softplus_tab_finite(xj - p.shift, th.ltab);
     double l[kNP];
 #pragma unroll
     for (int j = 0; j < kNP; ++j) l[j] = __shfl_sync(0xffffffffu, lj, (lane & ~3) | j);
@@ -147,11 +148,12 @@ __device__ __forceinline__ void mom_cta_points(const MomParams& p, const MomCtaT
     const double rv = rcp_fast2(v);
     const double rsd = rsqrt_fast2(v);
     const double res = y - ms;
-    const double t = res * rsd;
-    const double pdf = exp_fast_t<false>(-0.5 * (t * t)) * (rsd * kInvSqrt2Pi);
-    const double wgt = SINGLE ? th.wn0 : (act ? p.wn[s] : 0.0);
-    const double wp = wgt * pdf;                     // inactive threads: weight 0, finite pdf
+    // exp(-(y-m)^2 / (2v)) with the argument formed from 1/v: that reciprocal's chain is two instructions shorter than
+    // 1/sqrt(v)'s, which is only needed for the prefactor and finishes while the exponential runs
     const double q = res * rv;
+    const double ex = exp_fast_t<false>((-0.5 * res) * q);
+    const double wgt = SINGLE ? th.wn0 : (act ? p.wn[s] : 0.0);
+    const double wp = ex * (wgt * (rsd * kInvSqrt2Pi));     // inactive threads: weight 0, finite density
     const double c1 = wp * q;
     const double c2 = wp * fma(q, q, -rv);
 #pragma unroll

@@ -147,3 +147,14 @@ def test_fastmath_accuracy(nsagp, gpu_lib):
     nz = lit != 0
     assert np.max(np.abs(sp[nz] - lit[nz]) / np.abs(lit[nz])) < 1e-15
     assert np.all(sp[~nz] == 0.0)
+    # the table-driven logarithm of the moment warps (no division on the chain; op 9) and the link built on it (op 10)
+    lt = _fast(gpu_lib, nsagp, 9, u)
+    nz = ref != 0
+    assert np.max(np.abs(lt[nz] - ref[nz]) / np.abs(ref[nz])) < 1e-15 and _ulps(lt[nz], ref[nz]) <= 2
+    assert np.all(lt[~nz] == 0.0)
+    near1 = 1.0 + np.exp(rng.uniform(np.log(2.3e-16), np.log(1e-2), 100000))          # results down to one ulp of 1
+    assert _ulps(_fast(gpu_lib, nsagp, 9, near1), np.log(near1.astype(ld)).astype(float)) <= 2
+    st = _fast(gpu_lib, nsagp, 10, xs)
+    nz = lit != 0
+    assert np.max(np.abs(st[nz] - lit[nz]) / np.abs(lit[nz])) < 1e-15
+    assert np.all(st[~nz] == 0.0)
