@@ -151,7 +151,7 @@ __device__ __forceinline__ void mom_cta_points(const MomParams& p, const MomCtaT
     // exp(-(y-m)^2 / (2v)) with the argument formed from 1/v: that reciprocal's chain is two instructions shorter than
     // 1/sqrt(v)'s, which is only needed for the prefactor and finishes while the exponential runs
     const double q = res * rv;
-    const double ex = exp_fast_t<false>((-0.5 * res) * q);
+    const double ex = exp_fast_sel((-0.5 * res) * q);
     const double wgt = SINGLE ? th.wn0 : (act ? p.wn[s] : 0.0);
     const double wp = ex * (wgt * (rsd * kInvSqrt2Pi));     // inactive threads: weight 0, finite density
     const double c1 = wp * q;
@@ -252,11 +252,12 @@ __device__ __forceinline__ void adf_site_from_sums(double Zs, double r1, double 
   const double Nn = fma(r2, Zm, -r1 * r1);
   const double den = fma(Nn, s2, Zm * Zm);
   const double num_t = fma(r1, Zm, -mu * Nn);
-  if (fabs(den) > 1e-280 && fabs(den) < 1e280) {    // ordinary number: straight-line reciprocal
-    const double rd = rcp_fast2(den);
-    tt_new = -Nn * rd;
-    tn_new = num_t * rd;
-  } else {                                          // 0, Inf, NaN: IEEE division semantics
+  // straight-line reciprocal first (den is an ordinary number in all but degenerate steps); the range test depends on
+  // den alone, so it resolves while the reciprocal's chain runs and costs nothing on it
+  const double rd = rcp_fast2(den);
+  tt_new = -Nn * rd;
+  tn_new = num_t * rd;
+  if (!(fabs(den) > 1e-280 && fabs(den) < 1e280)) { // 0, Inf, NaN, subnormal: IEEE division semantics
     tt_new = -Nn / den;
     tn_new = num_t / den;
   }
