@@ -412,9 +412,14 @@ def run_gpu(args):
                 extras[name] = fn()
             except Exception as e:                       # an extra workload must never take the headline line down
                 extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
-                if dist is not None:
-                    raise
             L.nsagp_release_cache()
+            if dist is not None:
+                # a failure is symmetric (a rank that loses its peer times out in the exchange kernel after 10 s and
+                # raises too), so every rank arrives here; meet again before the next workload
+                try:
+                    dist.barrier()
+                except Exception as e:
+                    extras.setdefault(name, {})["barrier_error"] = "%s: %s" % (type(e).__name__, e)
         extras["wall_s"] = time.perf_counter() - t_ex
     if rank == 0:
         if extras:
