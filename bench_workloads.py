@@ -157,7 +157,7 @@ def one_signal_chunked(ctx, kind, T, itts, seed, reps=2, warm=1, chunks_per_gpu=
     return res
 
 
-def c5_batch(ctx, reps=2, warm=1, B=256, T=39062, n_clips=32):
+def c5_batch(ctx, reps=2, warm=1, B=256, T=39062, n_clips=32, adf_form=None):
     """256 (clip, hyper-parameter point) problems in nlZ mode, 10 M time steps in total, contiguous shards per rank."""
     nsagp, lm = ctx.nsagp, ctx.lm
     t0 = time.perf_counter()
@@ -192,6 +192,8 @@ def c5_batch(ctx, reps=2, warm=1, B=256, T=39062, n_clips=32):
         tabs = [p[0][1][1] for p in probs] if kind == lm.KIND_IHGP else None
         liks = [(mom, np.log([p[0][0].w_lik]), p[0][0].W) for p in probs]
         with nsagp.Plan(kind, models, liks, ALPHA, np.linspace(0.1, 0.1, itts), itts, ys, lm.MODE_NLZ, tables=tabs) as plan:
+            if adf_form is not None:
+                plan.set_adf_form(adf_form)
             ms = []
             for i in range(warm + reps):
                 ctx.barrier()
@@ -201,7 +203,8 @@ def c5_batch(ctx, reps=2, warm=1, B=256, T=39062, n_clips=32):
             t = ctx.max_over_ranks([np.mean(ms)])[0]
             sweeps = max(1, itts - 1)
             out[name] = {"ms": t, "steps_per_s": B * T * sweeps / t * 1e3, "sweeps_counted": sweeps,
-                         "edata_first": plan.fetch(0, ("edata",))["edata"]}
+                         "edata_first": plan.fetch(0, ("edata",))["edata"],
+                         "edata_last": plan.fetch(len(probs) - 1, ("edata",))["edata"]}
     return out
 
 

@@ -257,8 +257,12 @@ int nsagp_plan_create(nsagp_plan** plan, int32_t kind, int32_t B, const nsagp_mo
 int nsagp_plan_keep_pf(nsagp_plan* plan, int keep);
 /* Form of the sequential (ADF) filter pass, the only part of the schedule that is a
  * nonlinear recurrence in time (ihgp_ep_modulator_nmf.m:253-271, gf_ep_modulator_nmf.m:141-156):
- * 0 = one CTA per problem (default; lowest latency per step, for few long signals),
- * 1 = one warp per problem (for batches of many more problems than SMs). */
+ * 0 = one CTA per problem, its width chosen by the size of the launch (default): full width (one CTA per SM, lowest
+ *     latency per step) while there are no more problems than SMs, half width (form 2) beyond,
+ * 1 = one warp per problem (first-generation kernel with library arithmetic; kept as an independent implementation),
+ * 2 = one CTA per problem with half the moment threads and the steady-state tables left in HBM / L1, so that two CTAs
+ *     share an SM: one problem's Kalman section overlaps the other's cubature (256 problems on 148 SMs: 1.39x),
+ * 3 = full-width CTAs whatever the batch size. */
 int nsagp_plan_set_adf_form(nsagp_plan* plan, int form);
 int nsagp_plan_run(nsagp_plan* plan);
 int nsagp_plan_fetch(nsagp_plan* plan, int32_t b, nsagp_outputs* out);

@@ -211,7 +211,7 @@ struct nsagp_plan {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> phase_ev;
   double timings[5] = {0, 0, 0, 0, 0};
-  int adf_form = 0;             // 0: one CTA per signal (latency), 1: one warp per signal (many signals)
+  int adf_form = 0;             // 0: CTA per signal, width by the size of the launch; 1: warp per signal; 2: half-width CTA, two per SM; 3: full-width CTA
   int adf_chunks = 0;           // > 1: first filter pass parallel in time, burn-in overlap (opt-in, approximate; adfcta.cuh AdfPar)
   long long adf_burn = 0;
   double* d_bstate = nullptr;   // [B][adf_chunks][n] state at the end of each chunk's burn-in
@@ -714,7 +714,7 @@ int nsagp_release_cache(void) {
 
 int nsagp_plan_set_adf_form(nsagp_plan* pl, int form) {
   if (!pl) return fail(NSAGP_ERR_INVALID, "null plan");
-  if (form != 0 && form != 1) return fail(NSAGP_ERR_INVALID, "adf form must be 0 (CTA per signal) or 1 (warp per signal)");
+  if (form < 0 || form > 3) return fail(NSAGP_ERR_INVALID, "adf form must be 0 (automatic), 1 (warp per signal), 2 (half-width CTA, two per SM) or 3 (full-width CTA)");
   pl->adf_form = form;
   return NSAGP_OK;
 }
@@ -859,10 +859,29 @@ struct AdfGeom {
   bool tab_smem;
 };
 
-AdfGeom adf_geom(const nsagp_plan* pl, bool want_tables, bool fullstate) {
+static int sm_count() {
+  static thread_local int dev_cached = -1, n_cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) {
+    cudaDeviceGetAttribute(&n_cached, cudaDevAttrMultiProcessorCount, dev);
+    dev_cached = dev;
+  }
+  return n_cached > 0 ? n_cached : 148;
+}
+
+// nblocks: CTAs of the launch (problems x chunks of the parallel first pass)
+AdfGeom adf_geom(const nsagp_plan* pl, bool want_tables, bool fullstate, long long nblocks) {
   AdfGeom g;
   const int want = ((4 * pl->S + 31) / 32) * 32;
-  const int nmt = std::min(want, kAdfMaxMomThreads);      // moment threads
+  int nmt = std::min(want, kAdfMaxMomThreads);            // moment threads
+  // form 2 (batches of more problems than SMs): half the moment threads (each takes two sigma points per step) and the
+  // steady-state tables left in HBM / L1, so that TWO CTAs fit an SM (2 x 192 threads x 164 registers) -- one problem's
+  // Kalman section runs while the other's moment warps integrate
+  // (C5, 256 problems on 148 SMs: 122 -> 88 ms, profiles/r3a_c5.jsonl; with at most one problem per SM the full-width CTA is
+  // 1.3x faster, so form 0 picks by the size of the launch)
+  const bool half = pl->adf_form == 2 || (pl->adf_form == 0 && nblocks > sm_count());
+  if (half) { nmt = std::max(32, ((nmt / 2 + 31) / 32) * 32); want_tables = false; }
   g.threads = 32 + nmt;                                   // + the Kalman warp
   g.single = 4 * pl->S <= nmt;
   g.dpt = (pl->D <= 16) ? 4 : 8;
@@ -898,7 +917,7 @@ int adf_mismatch(nsagp_plan* pl, const AdfPar& par, int nch) {
 int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double damp, int running, bool parallel = false) {
   AdfPar par{0, 0, 0, 0, nullptr};
   int nch = 1;
-  if (parallel && pl->adf_chunks > 1 && pl->adf_form == 0 && mom_all && !running) par = adf_par(pl, k0, k1, nch);
+  if (parallel && pl->adf_chunks > 1 && pl->adf_form != 1 && mom_all && !running) par = adf_par(pl, k0, k1, nch);
   if (pl->adf_form == 1) {
     const size_t sm = 64 * sizeof(double) + lik_smem_bytes(pl);
     DISPATCH_DP(pl->DP, DISPATCH_BM(pl->BM, {
@@ -909,7 +928,7 @@ int ihgp_adf(nsagp_plan* pl, long long k0, long long k1, int mom_all, double dam
     LAUNCH_CHECK();
     return NSAGP_OK;
   }
-  const AdfGeom g = adf_geom(pl, k1 - k0 > 64, false);      // the table copy only pays off on a long pass
+  const AdfGeom g = adf_geom(pl, k1 - k0 > 64, false, (long long)pl->B * nch);      // the table copy only pays off on a long pass
   DISPATCH_DPT(g.dpt, DISPATCH_BM(pl->BM, DISPATCH_SINGLE(g.single, {
     if (g.tab_smem) {
       auto kern = ihgp_adf_cta_kernel<DPT_, BM_, SINGLE_, true>;

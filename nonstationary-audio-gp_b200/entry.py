@@ -152,7 +152,8 @@ class Plan:
         return self
 
     def set_adf_form(self, form):
-        """0: one CTA per problem (default), 1: one warp per problem (large batches)."""
+        """0: one CTA per problem, full width up to one problem per SM, half width (two CTAs per SM) beyond (default);
+        1: one warp per problem (first-generation kernel); 2 / 3: force half / full width."""
         _lib.check(_lib.lib().nsagp_plan_set_adf_form(self._h, int(form)))
         return self
 

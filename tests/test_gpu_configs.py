@@ -50,7 +50,7 @@ def _models(nsagp, pbs, kind_id, k1, k2, D, N, smoother=False):
     return models, liks, (tabs if kind_id == L.KIND_IHGP else None)
 
 
-@pytest.mark.parametrize("adf_form", [0, 1])
+@pytest.mark.parametrize("adf_form", [0, 1, 2, 3])
 def test_batch_ihgp_nlz_matches_per_problem_oracle(nsagp, gpu_lib, adf_form):
     from oracle import ihgp_ep
     L = nsagp._lib

@@ -40,7 +40,7 @@ def _dense_blocks(packed, sizes):
     return out
 
 
-@pytest.mark.parametrize("adf_form", [0, 1])      # one CTA per signal / one warp per signal
+@pytest.mark.parametrize("adf_form", [0, 1, 2])   # one CTA per signal / one warp per signal / half-width CTA (two per SM)
 @pytest.mark.parametrize("D,N,T,k1,k2,kind,p,shift,alpha,itts,gaps", CASES)
 def test_gfep_predict_matches_oracle(nsagp, gpu_lib, D, N, T, k1, k2, kind, p, shift, alpha, itts, gaps, adf_form):
     from oracle import gf_ep
