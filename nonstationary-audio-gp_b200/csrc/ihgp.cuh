@@ -293,7 +293,10 @@ struct FilterElem : AffineElemBase<BMS, BM> {
     l2_prefetch_bulk(St.R + k0 * P.M, bytes);
   }
   // Inputs of step k: the sites of steps k and k-1 (the look-up uses R(:,k-1), :239); table row of the look-up.
-  static constexpr int kPrefetch = 3;
+  // Ring depth 1 (the inputs of step s + 1 are requested before step s is processed): measured against 2, 3 and 4
+  // (profiles/r3c_ring.jsonl, r3d_ring.jsonl: 0.75 / 0.77 / 0.91 / 1.02 ms per 10^6 steps) -- every ring slot costs 10
+  // registers the walk does not have, and with the tile's rows on their way to L2 one step of lead is enough.
+  static constexpr int kPrefetch = 1;
   struct In { double tt, tn, R, ttp, Rp; };
   struct Tab { double w[BM], HPH; };
   __device__ __forceinline__ void load(long long k, In& in) const {
@@ -377,7 +380,7 @@ struct SmootherElem : AffineElemBase<BMS, BM> {
     if (apply) l2_prefetch_bulk(St.E + k_lo * P.M, (size_t)(k_hi - k_lo) * P.M * sizeof(double));
   }
   // Inputs of step k: R(:,k) (look-up of the smoother gain), the filtered mean, H*MS of the previous iteration.
-  static constexpr int kPrefetch = 3;
+  static constexpr int kPrefetch = 1;       // (see FilterElem)
   struct In { double R, ms[BM], Eold; };
   struct Tab { double G[BM * BM]; int idx; };
   __device__ __forceinline__ void load(long long k, In& in) const {
