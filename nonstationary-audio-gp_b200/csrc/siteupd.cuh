@@ -51,8 +51,11 @@ __host__ __device__ inline int site4_smem_doubles(int M, int S, int ndist, bool 
   return o;
 }
 
+// Launch bound: three CTAs per SM (154 registers).  Four (128 registers) measured the same on the infinite-horizon path
+// and 15 % slower on the full-state path, whose fifth staged array leaves room for three CTAs per SM anyway; five (96
+// registers, spills) 30 % slower (profiles/r3g_site.jsonl).
 template <int DPT, bool FULL, bool PAIR>
-__global__ void __launch_bounds__(kSiteThreads, DPT == 4 ? 4 : 2)
+__global__ void __launch_bounds__(kSiteThreads, DPT == 4 ? 3 : 2)
 site_update4_kernel(const DevProblem* __restrict__ probs, const DevState* __restrict__ states, long long k0, long long k1,
                     double alpha, double ep_damp, int write_lZ, int clamp_R) {
   const DevProblem& P = probs[blockIdx.y];
