@@ -43,7 +43,7 @@ K1, K2 = "exp", "matern52"
 ALPHA, SHIFT, P_CUB = 0.75, 1.0, 9
 EP_ITTS = 20
 # DRAM bytes per time step of the ADF kernel from the committed ncu --set full capture (profiles/); None = not captured
-TRAFFIC_ADF_BYTES_PER_STEP = (31.581696e6 + 24.212736e6) / 100000     # profiles/r1am_full.md (T = 100000; part of the writes was still in L2 when the kernel ended)
+TRAFFIC_ADF_BYTES_PER_STEP = (32.034560e6 + 24.303104e6) / 100000     # profiles/r2x_adf_full.md (T = 100000; part of the writes was still in L2 when the kernel ended)
 WORKLOAD = ("C2: ihgp_ep_modulator_nmf predict mode, D=16 exp subbands x N=3 matern52 modulators (n=41), "
             "likModulatorPreCalcwn p=9 (S=77), alpha=0.75, ep_itts=20, T=100000, 1 signal per GPU")
 
