@@ -1,0 +1,84 @@
+"""CPU: pin the oracle's tilted-distribution moments (oracle/lik.py, restating likModulatorNMFPower.m:28-87 and
+experiments/likModulatorPreCalcwn.m:28-86) against their DEFINITION, with no analytic marginalisation and no
+derivative formulas: Z(mu) = E_{z,g ~ N(mu, diag s2)}[ N(y | f(z,g), sn2)^alpha ] integrated by a dense product
+Gauss-Hermite rule over ALL of (z, g), dlZ and d2lZ as central differences of log Z in mu.  The reference ships no
+values for this path, so identities of this kind are what the oracle can be held to."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import cubature as oc
+from oracle import lik as ol
+
+Q = 40                                  # nodes per dimension of the oracle-side rule over g (converged to ~1e-12)
+QB = 36                                 # nodes per dimension of the brute-force rule over (z, g)
+
+
+def _brute_lZ(kind, link, sn2, alpha, y, mu, s2, W):
+    """log E[ p(y|z,g)^alpha ] (precalc: the power of the density itself; power: the reference drops the Power-EP
+    constant, likModulatorNMFPower.m:49, i.e. integrates N(y | f, sn2/alpha))."""
+    D, N = W.shape
+    t, w = np.polynomial.hermite_e.hermegauss(QB)
+    w = w / math.sqrt(2 * math.pi)
+    grids = np.meshgrid(*([np.arange(QB)] * (D + N)), indexing="ij")
+    x = np.stack([mu[i] + math.sqrt(s2[i]) * t[g.ravel()] for i, g in enumerate(grids)], axis=1)
+    wt = np.prod(np.stack([w[g.ravel()] for g in grids], axis=1), axis=1)
+    z, g = x[:, :D], x[:, D:]
+    a = link(g) @ W.T
+    if kind == "precalc":
+        a = np.sqrt(a)
+    f = np.sum(z * a, axis=1)
+    if kind == "precalc":
+        dens = (np.exp(-0.5 * (y - f) ** 2 / sn2) / math.sqrt(2 * math.pi * sn2)) ** alpha
+    else:
+        v = sn2 / alpha
+        dens = np.exp(-0.5 * (y - f) ** 2 / v) / math.sqrt(2 * math.pi * v)
+    return math.log(np.sum(wt * dens))
+
+
+def _oracle(kind, link, hyp, alpha, y, mu, s2, W):
+    N = W.shape[1]
+    if kind == "power":
+        return ol.likModulatorNMFPower(link, hyp, y, mu, s2, W, Q, alpha)
+    xn, wn = oc.mvhermgauss(np.zeros(N), np.ones(N), Q)
+    return ol.likModulatorPreCalcwn(link, hyp, y, mu, s2, W, alpha, wn, xn.T)
+
+
+@pytest.mark.parametrize("kind", ["power", "precalc"])
+@pytest.mark.parametrize("alpha", [1.0, 0.75])
+@pytest.mark.parametrize("shift", [0.0, 1.0])
+def test_moments_are_the_derivatives_of_the_tilted_normaliser(kind, alpha, shift):
+    rng = np.random.default_rng(11)
+    D, N = 2, 1
+    W = rng.uniform(0.3, 1.0, (D, N))
+    mu = np.concatenate([rng.normal(0, 0.5, D), rng.normal(0.3, 0.3, N)])
+    s2 = np.concatenate([rng.uniform(0.2, 0.5, D), rng.uniform(0.1, 0.3, N)])
+    sn2, y = 0.3, 0.4
+    link = ol.softplus_link(shift)
+    hyp = np.log([sn2])
+    lZ, dlZ, d2lZ = _oracle(kind, link, hyp, alpha, y, mu, s2, W)
+    b = lambda m: _brute_lZ(kind, link, sn2, alpha, y, m, s2, W)
+    assert abs(lZ - b(mu)) < 1e-9 * max(1.0, abs(lZ))
+    h = 1e-3
+    for i in range(D + N):
+        e = np.zeros(D + N); e[i] = h
+        lp, lm, l0 = b(mu + e), b(mu - e), b(mu)
+        # five-point stencils would be tighter; central differences at h = 1e-3 carry O(h^2) ~ 1e-6 truncation
+        assert abs(dlZ[i] - (lp - lm) / (2 * h)) < 5e-6 * max(1.0, abs(dlZ[i]))
+        assert abs(d2lZ[i] - (lp - 2 * l0 + lm) / h ** 2) < 5e-5 * max(1.0, abs(d2lZ[i]))
+
+
+def test_two_modulators_share_a_subband():
+    """N = 2 modulators mixed by W into D = 1 subband: the NMF product link(g) W' (likModulatorNMFPower.m:44)."""
+    rng = np.random.default_rng(5)
+    W = rng.uniform(0.3, 1.0, (1, 2))
+    mu = np.array([0.4, -0.2, 0.5]); s2 = np.array([0.3, 0.2, 0.15])
+    link = ol.softplus_link(1.0)
+    for kind in ("power", "precalc"):
+        lZ, dlZ, _ = _oracle(kind, link, np.log([0.2]), 0.75, 0.3, mu, s2, W)
+        b = lambda m: _brute_lZ(kind, link, 0.2, 0.75, 0.3, m, s2, W)
+        assert abs(lZ - b(mu)) < 1e-9
+        for i in range(3):
+            e = np.zeros(3); e[i] = 1e-3
+            assert abs(dlZ[i] - (b(mu + e) - b(mu - e)) / 2e-3) < 5e-6
