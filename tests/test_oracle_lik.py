@@ -82,3 +82,35 @@ def test_two_modulators_share_a_subband():
         for i in range(3):
             e = np.zeros(3); e[i] = 1e-3
             assert abs(dlZ[i] - (b(mu + e) - b(mu - e)) / 2e-3) < 5e-6
+
+
+def test_ep_with_the_real_likelihood_is_exact_gp_regression_when_the_modulator_is_frozen():
+    """One subband, one modulator whose prior variance is ~0: y_k = a z_k + noise with a = W softplus(0), so the whole
+    chain  cubature -> likModulatorNMFPower -> ADF filter -> RTS smoother  (gf_ep_modulator_nmf.m:126-267) must return
+    the dense GP-regression posterior of z and the Gaussian evidence of y."""
+    from oracle import gf_ep, ssmodel as oss
+    T, sn2 = 30, 0.05
+    ws = np.array([0.8, 12.0, 0.6])
+    wm = np.array([1e-12, 20.0])
+    F, L, Qc, H, Pinf = oss.ss_modulators_nmf(ws, wm, "matern32", "matern52")
+    A, Q = oss.lti_disc(F, L, Qc, 1.0)
+    n = A.shape[0]
+    W = np.array([[0.7]])
+    a = 0.7 * math.log(2.0)
+    rng = np.random.default_rng(3)
+    y = rng.normal(0, 0.5, T)
+    mom = ol.make_mom("power", ol.softplus_link(0.0), p=9)
+    Eft, Varft, lb, ub, out = gf_ep.gf_ep_core(A, Q, H, Pinf, np.log([sn2]), W, y, mom, 1.0, [1.0], 1, True, np.arange(T))
+    Apow = [np.eye(n)]
+    for _ in range(T):
+        Apow.append(A @ Apow[-1])
+    h = H[0]
+    K = np.array([[h @ (Apow[s - t] @ Pinf if s >= t else Pinf @ Apow[t - s].T) @ h for t in range(T)] for s in range(T)])
+    S = a * a * K + sn2 * np.eye(T)
+    mean = a * K @ np.linalg.solve(S, y)
+    var = np.diag(K - a * a * K @ np.linalg.solve(S, K))
+    assert np.allclose(Eft[0], mean, rtol=1e-7, atol=1e-9)
+    assert np.allclose(Varft[0], var, rtol=1e-7, atol=1e-9)
+    _, logdet = np.linalg.slogdet(S)
+    ref = -0.5 * y @ np.linalg.solve(S, y) - 0.5 * logdet - 0.5 * T * math.log(2 * math.pi)
+    assert abs(-out["nlZ"][0] - ref) < 1e-7 * abs(ref)
