@@ -11,14 +11,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def exact_case(nsagp, T=40, sn2=0.05, seed=3):
+def exact_case(nsagp, T=40, sn2=0.05, seed=3, a=None):
     from oracle import ssmodel as oss
     hyp = nsagp.synth.Hypers(sn2, var_fast=np.array([0.8]), len_fast=np.array([12.0]), omega=np.array([0.6]),
                              var_slow=np.array([1e-12, 1e-12]), len_slow=np.array([20.0, 35.0]), W=np.array([[0.7, 0.4]]))
     F, L, Qc, H, Pinf = oss.ss_modulators_nmf(hyp.w_sub(), hyp.w_mod(), "matern32", "matern52")
     A, Q = oss.lti_disc(F, L, Qc, 1.0)
     n = A.shape[0]
-    a = (0.7 + 0.4) * math.log(2.0)
+    a = (0.7 + 0.4) * math.log(2.0) if a is None else a
     y = np.random.default_rng(seed).normal(0, 0.5, T)
     Apow = [np.eye(n)]
     for _ in range(T):
@@ -49,3 +49,35 @@ def test_gfep_equals_dense_gp_regression_with_frozen_modulators(nsagp, gpu_lib, 
     # of y, the oracle shows the same offset -- the posterior above stays
     # exact because at alpha = 1 the sites of a Gaussian likelihood are a fixed point of the update
     assert abs(-np.asarray(out["nlZ"]).ravel()[0] - lml) < 1e-6 * abs(lml)
+
+
+@pytest.mark.parametrize("itts", [1, 3])
+def test_gfep_power_ep_posterior_is_exact_for_a_gaussian_likelihood(nsagp, gpu_lib, itts):
+    """likModulatorPreCalcwn ("sqrt" model, shifted link, alpha = 0.75): a = sqrt(sum_n W_n softplus(-1)).  Power EP
+    reproduces a Gaussian factor exactly whatever alpha is, so the posterior is still the GP regression (the Power-EP
+    energy is not the evidence, so nlZ is not compared)."""
+    a = math.sqrt((0.7 + 0.4) * math.log1p(math.exp(-1.0)))
+    hyp, y, mean, var, _ = exact_case(nsagp, a=a)
+    T = y.size
+    t = np.arange(1.0, T + 1.0)
+    wn, xn = nsagp.utp_ws(9, 2)
+    mom = nsagp.likModulatorPreCalcwn(nsagp.Softplus(1.0), wn, xn)
+    ss = lambda x, p1, p2, k1, k2: nsagp.ss_modulators_nmf(p1, p2, k1, k2)
+    E, V, _, _, _, out = nsagp.gf_ep_modulator_nmf(hyp.pack_log(), t, y, ss, mom, t, "matern32", "matern52", 1, 1, 2,
+                                                  0.75, np.ones(itts), itts)
+    assert np.allclose(E[0], mean, rtol=1e-6, atol=1e-8)
+    assert np.allclose(V[0], var, rtol=1e-6, atol=1e-8)
+
+
+def test_giekf_is_the_kalman_smoother_of_the_linear_model(nsagp, gpu_lib):
+    """gf_giekf_modulator_nmf with one global and one local iteration on the same frozen-modulator model: the
+    linearisation is exact, so the smoothed z is the GP regression and the energy is minus the Gaussian evidence."""
+    hyp, y, mean, var, lml = exact_case(nsagp)
+    T = y.size
+    t = np.arange(1.0, T + 1.0)
+    ss = lambda x, p1, p2, k1, k2: nsagp.ss_modulators_nmf(p1, p2, k1, k2)
+    E, V = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, t, "matern32", "matern52", 1, 1, 2, 1, 1)[:2]
+    assert np.allclose(E[0], mean, rtol=1e-6, atol=1e-8)
+    assert np.allclose(V[0], var, rtol=1e-6, atol=1e-8)
+    e = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, None, "matern32", "matern52", 1, 1, 2, 1, 1)[0]
+    assert abs(e + lml) < 1e-6 * abs(lml)
