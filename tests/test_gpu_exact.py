@@ -81,3 +81,52 @@ def test_giekf_is_the_kalman_smoother_of_the_linear_model(nsagp, gpu_lib):
     assert np.allclose(V[0], var, rtol=1e-6, atol=1e-8)
     e = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, None, "matern32", "matern52", 1, 1, 2, 1, 1)[0]
     assert abs(e + lml) < 1e-6 * abs(lml)
+
+
+def exact_case_subbands(nsagp, D=4, T=36, sn2=0.02, seed=9, k1="exp", k2="matern52"):
+    """D subbands, N = 2 frozen modulators: y = sum_d a_d z_d + noise, a_d = sum_n W_dn log 2.  Exact for the EKF's joint
+    update (not for EP, whose sites factorise over the latents)."""
+    from oracle import ssmodel as oss
+    rng = np.random.default_rng(seed)
+    hyp = nsagp.synth.Hypers(sn2, var_fast=rng.uniform(0.3, 1.0, D), len_fast=rng.uniform(5.0, 30.0, D),
+                             omega=np.linspace(1.0, 0.2, D), var_slow=np.array([1e-12, 1e-12]),
+                             len_slow=np.array([20.0, 35.0]), W=rng.uniform(0.2, 1.0, (D, 2)))
+    F, L, Qc, H, Pinf = oss.ss_modulators_nmf(hyp.w_sub(), hyp.w_mod(), k1, k2)
+    A, Q = oss.lti_disc(F, L, Qc, 1.0)
+    n = A.shape[0]
+    a = hyp.W.sum(axis=1) * math.log(2.0)
+    y = rng.normal(0, 0.5, T)
+    Apow = [np.eye(n)]
+    for _ in range(T):
+        Apow.append(A @ Apow[-1])
+    C = lambda s, t: Apow[s - t] @ Pinf if s >= t else Pinf @ Apow[t - s].T
+    Kd = [np.array([[H[d] @ C(s, t) @ H[d] for t in range(T)] for s in range(T)]) for d in range(D)]
+    S = sum(a[d] ** 2 * Kd[d] for d in range(D)) + sn2 * np.eye(T)
+    mean = np.stack([a[d] * Kd[d] @ np.linalg.solve(S, y) for d in range(D)])
+    var = np.stack([np.diag(Kd[d] - a[d] ** 2 * Kd[d] @ np.linalg.solve(S, Kd[d])) for d in range(D)])
+    _, logdet = np.linalg.slogdet(S)
+    lml = -0.5 * y @ np.linalg.solve(S, y) - 0.5 * logdet - 0.5 * T * math.log(2 * math.pi)
+    return hyp, y, mean, var, lml
+
+
+@pytest.mark.parametrize("D,k1", [(4, "exp"), (6, "matern32")])
+def test_giekf_joint_update_is_exact_over_several_subbands(nsagp, gpu_lib, D, k1):
+    hyp, y, mean, var, lml = exact_case_subbands(nsagp, D=D, k1=k1)
+    T = y.size
+    t = np.arange(1.0, T + 1.0)
+    ss = lambda x, p1, p2, k1_, k2_: nsagp.ss_modulators_nmf(p1, p2, k1_, k2_)
+    E, V = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, t, k1, "matern52", 1, D, 2, 1, 1)[:2]
+    assert np.allclose(E[:D], mean, rtol=1e-6, atol=1e-8)
+    assert np.allclose(V[:D], var, rtol=1e-6, atol=1e-8)
+    e = nsagp.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, None, k1, "matern52", 1, D, 2, 1, 1)[0]
+    assert abs(e + lml) < 1e-6 * abs(lml)
+
+
+def test_gfep_nlz_mode_returns_the_gaussian_evidence(nsagp, gpu_lib):
+    """xt empty: the entry point's first output is nlZ (gf_ep_modulator_nmf.m:357-533)."""
+    hyp, y, _, _, lml = exact_case(nsagp)
+    t = np.arange(1.0, y.size + 1.0)
+    mom = nsagp.likModulatorNMFPower(nsagp.Softplus(0.0), 9, 2)
+    ss = lambda x, p1, p2, k1, k2: nsagp.ss_modulators_nmf(p1, p2, k1, k2)
+    nlZ = nsagp.gf_ep_modulator_nmf(hyp.pack_log(), t, y, ss, mom, None, "matern32", "matern52", 1, 1, 2, 1.0, np.ones(1), 1)[0]
+    assert abs(float(np.ravel(nlZ)[0]) + lml) < 1e-6 * abs(lml)

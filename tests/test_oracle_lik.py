@@ -114,3 +114,29 @@ def test_ep_with_the_real_likelihood_is_exact_gp_regression_when_the_modulator_i
     _, logdet = np.linalg.slogdet(S)
     ref = -0.5 * y @ np.linalg.solve(S, y) - 0.5 * logdet - 0.5 * T * math.log(2 * math.pi)
     assert abs(-out["nlZ"][0] - ref) < 1e-7 * abs(ref)
+
+
+def test_oracle_entry_points_are_exact_on_the_frozen_modulator_models(nsagp):
+    """The same closed-form cases the CUDA path is held to in tests/test_gpu_exact.py, for the oracle: Power EP
+    (alpha = 0.75, sqrt model) posterior, the EKF entry point over several subbands (posterior + energy), the nlZ mode."""
+    from test_gpu_exact import exact_case, exact_case_subbands
+    from oracle import gf_ep, giekf, ssmodel as oss
+    ss = lambda x, p1, p2, k1, k2: oss.ss_modulators_nmf(p1, p2, k1, k2)
+    a = math.sqrt(1.1 * math.log1p(math.exp(-1.0)))
+    hyp, y, mean, var, _ = exact_case(nsagp, a=a)
+    t = np.arange(1.0, y.size + 1.0)
+    wn, xn = oc.utp_ws(9, 2)
+    mom = ol.make_mom("precalc", ol.softplus_link(1.0), wn=wn, xn_unscaled=xn)
+    E, V = gf_ep.gf_ep_modulator_nmf(hyp.pack_log(), t, y, ss, mom, t, "matern32", "matern52", 1, 1, 2, 0.75, np.ones(3), 3)[:2]
+    assert np.allclose(E[0], mean, rtol=1e-8, atol=1e-10) and np.allclose(V[0], var, rtol=1e-8, atol=1e-10)
+    hyp, y, mean, var, lml = exact_case_subbands(nsagp, D=4, k1="exp")
+    t = np.arange(1.0, y.size + 1.0)
+    E, V = giekf.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, t, "exp", "matern52", 1, 4, 2, 1, 1)[:2]
+    assert np.allclose(E[:4], mean, rtol=1e-8, atol=1e-10) and np.allclose(V[:4], var, rtol=1e-8, atol=1e-10)
+    e = giekf.gf_giekf_modulator_nmf(hyp.pack_log(), t, y, ss, None, None, "exp", "matern52", 1, 4, 2, 1, 1)[0]
+    assert abs(e + lml) < 1e-8 * abs(lml)
+    hyp, y, _, _, lml = exact_case(nsagp)
+    t = np.arange(1.0, y.size + 1.0)
+    mom = ol.make_mom("power", ol.softplus_link(0.0), p=9)
+    nlZ = gf_ep.gf_ep_modulator_nmf(hyp.pack_log(), t, y, ss, mom, None, "matern32", "matern52", 1, 1, 2, 1.0, np.ones(1), 1)[0]
+    assert abs(float(np.ravel(nlZ)[0]) + lml) < 1e-8 * abs(lml)
