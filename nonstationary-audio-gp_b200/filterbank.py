@@ -46,7 +46,7 @@ def kernel_ss_kalmanFastFB(A, Q, C, P0, K, vary, y, verbose=0, KF=0):
         PP = sla.solve_discrete_are(A.T, H.T, Q, np.array([[R]]))                # dare(A',H',Q,R) (:50)
     except Exception as e:
         raise RuntimeError("Unstable DARE solution! (%s)" % e)                    # :55-57
-    S = float(H @ PP @ H.T) + R
+    S = (H @ PP @ H.T).item() + R
     Kg = (PP @ H.T / S).ravel()
     AKHA = A - np.outer(Kg, H @ A)
     PF2 = PP - np.outer(Kg, H @ PP)

@@ -48,7 +48,7 @@ def kernel_ss_kalmanFastFB(A, Q, C, P0, K, vary, y, verbose=0, KF=0):
     R = float(vary)
     m = np.zeros(n)
     PP = sla.solve_discrete_are(A.T, H.T, Q, np.array([[R]]))                     # :50
-    S = float(H @ PP @ H.T) + R                                                   # :53
+    S = (H @ PP @ H.T).item() + R                                                   # :53
     Kg = (PP @ H.T / S).ravel()                                                   # :60
     AKHA = A - np.outer(Kg, H @ A)                                                # :63
     MS = np.zeros((n, T))

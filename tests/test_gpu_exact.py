@@ -130,3 +130,23 @@ def test_gfep_nlz_mode_returns_the_gaussian_evidence(nsagp, gpu_lib):
     ss = lambda x, p1, p2, k1, k2: nsagp.ss_modulators_nmf(p1, p2, k1, k2)
     nlZ = nsagp.gf_ep_modulator_nmf(hyp.pack_log(), t, y, ss, mom, None, "matern32", "matern52", 1, 1, 2, 1.0, np.ones(1), 1)[0]
     assert abs(float(np.ravel(nlZ)[0]) + lml) < 1e-6 * abs(lml)
+
+
+def test_filterbank_equals_the_time_varying_kalman_smoother_in_the_interior(nsagp, gpu_lib):
+    """kernel_ss_kalmanFastFB (stationary gains): away from the ends of a long signal its filter and smoother means are
+    those of the ordinary Kalman filter / RTS smoother of the same model (a textbook recursion, tests/test_oracle_filterbank.py)."""
+    import importlib
+    from test_oracle_filterbank import _kalman_rts
+    from conftest import rel_err
+    fb = importlib.import_module(nsagp.__name__ + ".filterbank")
+    rng = np.random.default_rng(1)
+    D, T = 3, 1200
+    lamx, varx, om = 1.0 / rng.uniform(20, 60, D), rng.uniform(0.3, 1.0, D), np.array([0.9, 0.5, 0.2])
+    A, Q, H, Pinf, K, tau = fb.get_disc_model(lamx, varx, om, D, "matern32")
+    y = np.cos(0.5 * np.arange(T)) + 0.1 * rng.standard_normal(T)
+    MF, MS = _kalman_rts(A, Q, H, Pinf, 0.01, y)
+    _, Xf, _ = fb.kernel_ss_kalmanFastFB(A, Q, H, Pinf, K, 0.01, y, 0, 1)
+    _, Xs, _ = fb.kernel_ss_kalmanFastFB(A, Q, H, Pinf, K, 0.01, y, 0, 0)
+    mid = slice(500, 700)
+    assert rel_err(Xf[0][:, mid], MF[:, mid]) < 1e-6
+    assert rel_err(Xs[0][:, mid], MS[:, mid]) < 1e-6

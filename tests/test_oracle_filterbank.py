@@ -15,9 +15,9 @@ def _kalman_rts(A, Q, H, Pinf, R, y):
     for k in range(T):
         m, P = A @ m, A @ P @ A.T + Q
         if not np.isnan(y[k]):
-            S = float(H @ P @ H.T) + R
+            S = (H @ P @ H.T).item() + R
             K = (P @ H.T / S).ravel()
-            m = m + K * (y[k] - float(H @ m))
+            m = m + K * (y[k] - (H @ m).item())
             P = P - np.outer(K, H @ P)
         MF[:, k], PF[:, :, k] = m, P
     MS = MF.copy()
