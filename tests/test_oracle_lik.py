@@ -140,3 +140,33 @@ def test_oracle_entry_points_are_exact_on_the_frozen_modulator_models(nsagp):
     mom = ol.make_mom("power", ol.softplus_link(0.0), p=9)
     nlZ = gf_ep.gf_ep_modulator_nmf(hyp.pack_log(), t, y, ss, mom, None, "matern32", "matern52", 1, 1, 2, 1.0, np.ones(1), 1)[0]
     assert abs(float(np.ravel(nlZ)[0]) + lml) < 1e-8 * abs(lml)
+
+
+def test_oracle_non_nmf_entry_point_is_exact_with_a_frozen_modulator():
+    """gf_ep_modulator.m (no NMF weights, balanced model, likModulatorPower): one carrier x modulator pair whose
+    modulator has prior variance ~0 is y = log(2) z + noise; the balancing transformation must not change the answer."""
+    from oracle import gf_ep, ssmodel as oss
+    T, sn2 = 30, 0.05
+    par = np.array([0.8, 12.0, 0.6, 1e-12, 20.0])
+    w = np.log(np.concatenate([[sn2], par]))
+    F, L, Qc, H, Pinf = oss.ss_modulators(par, "matern32", "matern52")[:5]
+    A, Q = oss.lti_disc(F, L, Qc, 1.0)
+    n = A.shape[0]
+    a = math.log(2.0)
+    y = np.random.default_rng(8).normal(0, 0.5, T)
+    t = np.arange(1.0, T + 1.0)
+    link = ol.softplus_link(0.0)
+    mom = lambda hyp, mu, s2, ep_frac, yall, k: ol.likModulatorPower(link, hyp, yall[k], mu, s2, 9, ep_frac)
+    ss = lambda x, pr, k1, k2: oss.ss_modulators(pr, k1, k2)
+    E, V, _, _, _, out = gf_ep.gf_ep_modulator(w, t, y, ss, mom, t, "matern32", "matern52", 1, 1.0, np.ones(2), 2)
+    Apow = [np.eye(n)]
+    for _ in range(T):
+        Apow.append(A @ Apow[-1])
+    h = H[0]
+    K = np.array([[h @ (Apow[s - u] @ Pinf if s >= u else Pinf @ Apow[u - s].T) @ h for u in range(T)] for s in range(T)])
+    S = a * a * K + sn2 * np.eye(T)
+    assert np.allclose(E[0], a * K @ np.linalg.solve(S, y), rtol=1e-7, atol=1e-9)
+    assert np.allclose(V[0], np.diag(K - a * a * K @ np.linalg.solve(S, K)), rtol=1e-7, atol=1e-9)
+    _, logdet = np.linalg.slogdet(S)
+    ref = -0.5 * y @ np.linalg.solve(S, y) - 0.5 * logdet - 0.5 * T * math.log(2 * math.pi)
+    assert abs(-out["nlZ"][0] - ref) < 1e-7 * abs(ref)
