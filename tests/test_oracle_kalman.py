@@ -208,3 +208,20 @@ def test_ihgp_smoother_tables_follow_the_reference_not_the_textbook():
     v_tab = hb @ tabs["PGlist"][0][j][:b * b].reshape((b, b), order="F") @ hb
     assert abs(v_tab - v_ref) < 2e-2 * v_ref
     assert v_ref > 1.1 * v_text                               # 22 % here; 2.8x at R = 0.086
+
+
+def test_ihgp_filter_side_agrees_with_the_full_path_on_constant_sites(nsagp):
+    """The other half of F14: on the frozen-modulator model the infinite-horizon FILTER follows the full-covariance one
+    to the resolution of its 32-node tables, and both find the exact Gaussian site 1/ttau = sn2/a^2."""
+    from test_gpu_exact import exact_case
+    hyp, y, _, _, _ = exact_case(nsagp, T=400)
+    t = np.arange(1.0, y.size + 1.0)
+    ss = lambda x, p1, p2, k1, k2: oss.ss_modulators_nmf(p1, p2, k1, k2)
+    mom = olik.make_mom("power", olik.softplus_link(0.0), p=9)
+    a = (t, y, ss, mom, t, "matern32", "matern52", 1, 1, 2, 1.0, np.ones(1), 1)
+    oi = ihgp_ep.ihgp_ep_modulator_nmf(hyp.pack_log(), *a)[5]
+    of = gf_ep.gf_ep_modulator_nmf(hyp.pack_log(), *a)[5]
+    mid = slice(150, 250)
+    R = 0.05 / (1.1 * math.log(2.0)) ** 2
+    assert np.allclose(1 / oi["ttau"][0, mid], R, rtol=1e-9) and np.allclose(1 / of["ttau"][0, mid], R, rtol=1e-9)
+    assert np.max(np.abs(oi["MF"][0, mid] - of["MF"][0, mid])) < 5e-3 * np.max(np.abs(of["MF"][0, mid]))
